@@ -1,0 +1,138 @@
+/* sevenn_b200 -- C ABI of the B200-native SevenNet energy/force engine.
+ *
+ * Plain pointers and sizes only (no torch / C++ types): this is the boundary a maintainer of
+ * the reference binds with ctypes / cgo-style FFI.  All device pointers
+ * are CUDA device memory on the current device; `stream` is a cudaStream_t passed as void*.
+ * Every function returns 0 on success and non-zero on error; s7b_last_error() then returns a
+ * human-readable message (thread-local).
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   - the TP-accelerator plug-in `convolution_cls`
+ *       sevenn/nn/convolution.py:243-247,270-276 (call contract)
+ *       sevenn/nn/flash_helper.py:33-48, sevenn/nn/oeq_helper.py:30-70 (existing adapters)
+ *       sevenn/pair_e3gnn/pair_e3gnn_oeq_autograd.cpp:23-27,64-133 (C++ fwd/bwd op signatures)
+ *     -> s7b_conv_plan_create / s7b_conv_forward / s7b_conv_backward
+ *   - the model forward + autograd force path executed per MD step by
+ *       sevenn/calculator.py:219-233 (SevenNetCalculator.calculate)
+ *       sevenn/pair_e3gnn/pair_e3gnn.cpp:74-289 (PairE3GNN::compute: edges in, E/F/virial out)
+ *     -> s7b_engine_* (device-resident graph) and s7b_engine_compute_host (host buffers)
+ *   - the per-layer segments + ghost exchange hooks of
+ *       sevenn/pair_e3gnn/pair_e3gnn_parallel.cpp:345-441 (segment forward / manual backward)
+ *     -> s7b_engine_run_stage + s7b_engine_buffer (the caller exchanges ghost rows between stages)
+ */
+#ifndef SEVENN_B200_H
+#define SEVENN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define S7B_API __attribute__((visibility("default")))
+#else
+#define S7B_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S7B_MAX_LAYERS 8
+#define S7B_MAX_L 4 /* l = 0..3 */
+
+typedef struct S7bEngine S7bEngine;
+typedef struct S7bConvPlan S7bConvPlan;
+
+/* Model architecture (even-parity NequIP-type SevenNet; sevenn/model_build.py:448-616). */
+typedef struct {
+  int32_t n_layers;                                   /* interaction layers (5 for SevenNet-0) */
+  int32_t lmax_filter;                                /* spherical harmonics up to this l */
+  int32_t num_species;
+  int32_t n_basis;                                    /* Bessel functions (8) */
+  float cutoff;
+  int32_t cutoff_fn;                                  /* 0 = XPLOR, 1 = polynomial */
+  float cutoff_on;                                    /* XPLOR r_on */
+  int32_t poly_p;
+  int32_t radial_hidden[2];                           /* radial MLP hidden widths (64, 64) */
+  int32_t n_l[S7B_MAX_LAYERS + 1];                    /* number of l's of irreps t (t = n_layers: output) */
+  int32_t muls[S7B_MAX_LAYERS + 1][S7B_MAX_L];        /* multiplicity of l in irreps t */
+  int32_t table_knots;                                /* > 0: radial weights from cubic tables */
+} S7bModelDesc;
+
+/* Stages of one energy/force evaluation (single GPU: s7b_engine_compute runs them all).
+ * Multi-GPU callers run them one by one and exchange ghost rows in between:
+ *   FWD_BEGIN | for t: FWD_LAYER(t) [exchange ghost rows of x(t+1)] | FWD_END |
+ *   for t = T-1..0: BWD_LAYER_A(t) [reverse-add ghost rows of dx(t)] BWD_LAYER_B(t) |
+ *   BWD_END [reverse-add ghost rows of forces]                                               */
+enum {
+  S7B_STAGE_FWD_BEGIN = 0,
+  S7B_STAGE_FWD_LAYER = 1,
+  S7B_STAGE_FWD_END = 2,
+  S7B_STAGE_BWD_LAYER_A = 3,
+  S7B_STAGE_BWD_LAYER_B = 4,
+  S7B_STAGE_BWD_END = 5
+};
+
+S7B_API const char* s7b_last_error(void);
+S7B_API int s7b_version(void);
+
+/* ---- engine ---------------------------------------------------------------------------- */
+S7B_API int s7b_engine_create(const S7bModelDesc* desc, S7bEngine** out);
+S7B_API void s7b_engine_destroy(S7bEngine* eng);
+
+/* Upload one named parameter array (host pointer, fp32).  Names: "embed_x0", "embed_g0",
+ * "readout", "scale", "shift", "bessel", and per layer t "si1", "si1T", "sc", "scT", "si2",
+ * "si2T", "table", "mlp0".."mlp2", "mlp0T".."mlp2T" (layouts: sevenn_b200/engine.py). */
+S7B_API int s7b_engine_set_param(S7bEngine* eng, const char* name, int layer, const float* host, size_t numel);
+
+/* Describe the graph of this step (device pointers, kept by reference until the next call).
+ * Nodes 0..n_local-1 are owned atoms, n_local..n_nodes-1 ghosts; edges are sorted by centre:
+ * rowptr[n_local+1] is the CSR over centres, src[e] in [0, n_nodes), edge_vec = r_src - r_centre. */
+S7B_API int s7b_engine_set_graph(S7bEngine* eng, int32_t n_nodes, int32_t n_local, int64_t n_edges,
+                         const int32_t* d_species, const int32_t* d_rowptr, const int32_t* d_src,
+                         const float* d_edge_vec, void* stream);
+
+S7B_API int s7b_engine_run_stage(S7bEngine* eng, int stage, int layer, void* stream);
+S7B_API int s7b_engine_compute(S7bEngine* eng, void* stream);
+
+/* Device pointer to an engine-owned buffer (valid until the next set_graph that grows it):
+ * "x" (layer t input after self_interaction_1, [n_nodes, dim_x(t)]), "dx", "gate_in", "mid",
+ * "h", "energy" (double[1]), "atomic_energy" [n_local], "forces" [n_nodes,3], "edge_force" [E,3],
+ * "virial" (double[6], = -sum r (x) f), "edge_Y", "edge_rec".  *numel receives the element count. */
+S7B_API void* s7b_engine_buffer(S7bEngine* eng, const char* name, int layer, size_t* numel);
+
+/* Host-buffer entry point, the analogue of PairE3GNN::compute (pair_e3gnn.cpp:74-289):
+ * edges as (centre, neighbour, vector) triples sorted by centre, H2D + all stages + D2H.
+ * forces: [n_nodes,3]; virial: 6 doubles (xx,yy,zz,xy,yz,zx of -sum r (x) f); atomic_energy may be NULL. */
+S7B_API int s7b_engine_compute_host(S7bEngine* eng, int32_t n_nodes, int64_t n_edges,
+                            const int32_t* species, const int32_t* edge_centre,
+                            const int32_t* edge_neighbour, const float* edge_vec, double* energy,
+                            float* atomic_energy, float* forces, double* virial, void* stream);
+
+/* Number of kernels this library launched since the last reset (bench.py's gpu_launches). */
+S7B_API int64_t s7b_launch_count(int reset);
+
+/* ---- operator-level plug-in: fused gather -> 'uvu' tensor product -> scatter ------------- */
+/* irreps of x as multiplicities per l (even parity), filter lmax, and lmax of the output; the
+ * instruction set is the complete triangle-allowed one of sevenn/nn/convolution.py:61-82.      */
+S7B_API int s7b_conv_plan_create(int32_t n_l_x, const int32_t* x_muls, int32_t lmax_filter,
+                         int32_t lmax_out, S7bConvPlan** out);
+S7B_API void s7b_conv_plan_destroy(S7bConvPlan* plan);
+S7B_API int s7b_conv_plan_dims(const S7bConvPlan* plan, int32_t* dim_x, int32_t* dim_mid, int32_t* weight_numel,
+                       int32_t* n_sh);
+
+/* All tensors in the engine's component-major layout (sevenn_b200/conv_op.py converts from
+ * e3nn mul_ir): x [n_nodes, dim_x], sh [E, n_sh] (incl. Y_0), weight [E, W], edges sorted by
+ * centre with rowptr [n_dst+1]; out [n_dst, dim_mid] is overwritten.  E == 0 is legal.          */
+S7B_API int s7b_conv_forward(const S7bConvPlan* plan, const float* x, const float* sh, const float* weight,
+                     const int32_t* rowptr, const int32_t* src, int32_t n_nodes, int32_t n_dst,
+                     int64_t n_edges, float* out, void* stream);
+/* grad_x [n_nodes, dim_x] (overwritten), grad_sh [E, n_sh], grad_weight [E, W]. */
+S7B_API int s7b_conv_backward(const S7bConvPlan* plan, const float* x, const float* sh, const float* weight,
+                      const int32_t* rowptr, const int32_t* src, int32_t n_nodes, int32_t n_dst,
+                      int64_t n_edges, const float* grad_out, float* grad_x, float* grad_sh,
+                      float* grad_weight, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEVENN_B200_H */

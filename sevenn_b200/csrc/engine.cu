@@ -1,0 +1,886 @@
+// Host side of the C ABI (include/sevenn_b200.h): model description -> per-layer launch plans,
+// device buffers, and the stage sequence of one energy/force evaluation.
+//
+// The stage sequence restates, with hand-written kernels and a hand-written backward, what the
+// reference executes per MD step through torch modules and autograd:
+//   AtomGraphSequential.forward          sevenn/nn/sequential.py:157-183
+//   NequIP_interaction_block order       sevenn/nn/interaction_blocks.py:41-76
+//   ForceStressOutputFromEdge            sevenn/nn/force_output.py:171-230
+//   segment-wise forward / backward      sevenn/pair_e3gnn/pair_e3gnn_parallel.cpp:345-441
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sevenn_b200.h"
+#include "common.cuh"
+#include "conv_kernels.cuh"
+#include "edge_kernels.cuh"
+#include "node_kernels.cuh"
+
+namespace s7b {
+
+static thread_local std::string g_error;
+static int64_t g_launches = 0;
+extern int64_t g_conv_launches;
+
+void set_error(const char* file, int line, const char* msg) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s:%d: %s", file, line, msg);
+  g_error = buf;
+}
+static int fail(const std::string& m) {
+  g_error = m;
+  return 1;
+}
+
+#define S7B_LAUNCH_CHECK()                          \
+  do {                                              \
+    ++g_launches;                                   \
+    S7B_CUDA_CHECK(cudaGetLastError());             \
+  } while (0)
+
+// ---- conv launch dispatch (defined in conv_dispatch_*.cu) ---------------------------------
+int launch_conv_fwd(int l1, int lf, int lo, bool table, const ConvArgs& a, const ConvRole& role,
+                    float* out, cudaStream_t st);
+int launch_conv_bwd(int l1, int lf, int lo, bool table, bool need_dx, const ConvArgs& a,
+                    const ConvRole& role, const float* gout, float* dx, float* dY_acc,
+                    float* dEdr_acc, float* dw, cudaStream_t st);
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = need + need / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+      cudaGetLastError();
+      return 1;
+    }
+    bytes = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PathCfg { int l1, l2, l3, mul, w_off, k_off; };
+
+struct LayerCfg {
+  int n_lx = 0, n_lg = 0;             // number of l's in x / gate-out irreps
+  int x_muls[kMaxL] = {0}, out_muls[kMaxL] = {0}, g_muls[kMaxL] = {0};
+  int x_off[kMaxL] = {0}, g_off[kMaxL] = {0}, h_off[kMaxL] = {0};
+  int dim_x = 0, dim_g = 0, dim_h = 0, dim_mid = 0, W = 0;
+  int mid_K[kMaxL] = {0}, mid_off[kMaxL] = {0};
+  int lmax_out = 0;
+  std::vector<PathCfg> paths;
+  ConvRole roles[kMaxL];
+  GateDesc gate;
+  std::map<std::string, DevBuf> params;
+};
+
+}  // namespace s7b
+
+using namespace s7b;
+
+struct S7bEngine {
+  S7bModelDesc desc;
+  std::vector<LayerCfg> layers;
+  std::map<std::string, DevBuf> params;   // global parameters
+  RadialDesc radial;
+  bool radial_ready = false;
+  int ny_stride = 8;
+  // graph
+  int n_nodes = 0, n_local = 0;
+  int64_t n_edges = 0;
+  const int* d_species = nullptr;
+  const int* d_rowptr = nullptr;
+  const int* d_src = nullptr;
+  const float* d_edge_vec = nullptr;
+  // per-step buffers
+  DevBuf rec, Y, rlen, emb, dY_acc, dEdr_acc, demb_acc, fedge;
+  std::vector<DevBuf> x, g, wbuf, z1, z2, h1, h2;   // per layer (wbuf.. exact-MLP mode only)
+  DevBuf mid, h, dh, dg, dx, dwbuf, tmpA, tmpB;
+  DevBuf energy, atomic_energy, forces, virial;
+  // host staging for compute_host
+  DevBuf hs_species, hs_rowptr, hs_src, hs_vec;
+  std::vector<int> host_rowptr;
+};
+
+struct S7bConvPlan {
+  LayerCfg cfg;
+  int lmax_filter = 0;
+  int ny_stride = 8;
+};
+
+namespace s7b {
+
+static int irreps_dim(const int* muls, int n_l) {
+  int d = 0;
+  for (int l = 0; l < n_l; ++l) d += (2 * l + 1) * muls[l];
+  return d;
+}
+
+// Restates build_layer() of sevenn_b200/spec.py (reference convolution.py:61-82 path order).
+static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* out_muls, int n_lo,
+                           int lmax_filter) {
+  L.n_lx = n_lx;
+  L.n_lg = n_lo;
+  L.lmax_out = n_lo - 1;
+  int off = 0;
+  for (int l = 0; l < n_lx; ++l) {
+    if (x_muls[l] % 32 != 0 || x_muls[l] <= 0) return fail("multiplicities must be positive multiples of 32");
+    L.x_muls[l] = x_muls[l];
+    L.x_off[l] = off;
+    off += (2 * l + 1) * x_muls[l];
+  }
+  L.dim_x = off;
+  int n_gates = 0;
+  for (int l = 1; l < n_lo; ++l) n_gates += out_muls[l];
+  for (int l = 0; l < n_lo; ++l) {
+    if (out_muls[l] % 32 != 0 || out_muls[l] <= 0) return fail("multiplicities must be positive multiples of 32");
+    L.out_muls[l] = out_muls[l];
+    L.g_muls[l] = out_muls[l] + (l == 0 ? n_gates : 0);
+  }
+  L.dim_g = irreps_dim(L.g_muls, n_lo);
+  L.dim_h = irreps_dim(L.out_muls, n_lo);
+  off = 0;
+  int hoff = 0;
+  for (int l = 0; l < n_lo; ++l) {
+    L.g_off[l] = off;
+    off += (2 * l + 1) * L.g_muls[l];
+    L.h_off[l] = hoff;
+    hoff += (2 * l + 1) * L.out_muls[l];
+  }
+  // paths: creation order (l1, l2, l3 ascending), then stable sort by l3
+  struct C { int l1, l2, l3, mul; };
+  std::vector<C> created;
+  for (int l1 = 0; l1 < n_lx; ++l1)
+    for (int l2 = 0; l2 <= lmax_filter; ++l2)
+      for (int l3 = abs(l1 - l2); l3 <= l1 + l2; ++l3)
+        if (l3 <= L.lmax_out) created.push_back({l1, l2, l3, x_muls[l1]});
+  std::vector<int> order;
+  for (int l3 = 0; l3 <= L.lmax_out; ++l3)
+    for (size_t c = 0; c < created.size(); ++c)
+      if (created[c].l3 == l3) order.push_back((int)c);
+  int w_off = 0;
+  int k_run[kMaxL] = {0, 0, 0, 0};
+  L.paths.clear();
+  for (int c : order) {
+    const C& q = created[c];
+    L.paths.push_back({q.l1, q.l2, q.l3, q.mul, w_off, k_run[q.l3]});
+    k_run[q.l3] += q.mul;
+    w_off += q.mul;
+  }
+  L.W = w_off;
+  off = 0;
+  for (int l = 0; l <= L.lmax_out; ++l) {
+    L.mid_K[l] = k_run[l];
+    L.mid_off[l] = off;
+    off += (2 * l + 1) * k_run[l];
+  }
+  L.dim_mid = off;
+  // conv roles: per l1 the paths in slot order
+  for (int l1 = 0; l1 < n_lx; ++l1) {
+    ConvRole& r = L.roles[l1];
+    memset(&r, 0, sizeof(r));
+    r.x_off = L.x_off[l1];
+    r.mul = x_muls[l1];
+    int p = 0;
+    for (const PathCfg& q : L.paths) {
+      if (q.l1 != l1) continue;
+      if (p >= kMaxPaths) return fail("too many paths for one l1");
+      r.w_off[p] = q.w_off;
+      r.out_off[p] = L.mid_off[q.l3] + q.k_off;
+      r.out_stride[p] = L.mid_K[q.l3];
+      ++p;
+    }
+  }
+  // gate
+  GateDesc& gd = L.gate;
+  memset(&gd, 0, sizeof(gd));
+  gd.n_scalars = out_muls[0];
+  gd.lmax = n_lo - 1;
+  gd.dim_g = L.dim_g;
+  gd.dim_h = L.dim_h;
+  int goff = out_muls[0];
+  for (int l = 0; l < kMaxL; ++l) {
+    gd.mul[l] = l < n_lo ? out_muls[l] : 0;
+    gd.g_off[l] = l < n_lo ? L.g_off[l] : L.dim_g;
+    gd.h_off[l] = l < n_lo ? L.h_off[l] : L.dim_h;
+    gd.gate_off[l] = L.g_muls[0];
+  }
+  for (int l = 1; l < n_lo; ++l) {
+    gd.gate_off[l] = goff;
+    goff += out_muls[l];
+  }
+  return 0;
+}
+
+static int launch_gemm(const LinArgs& a, cudaStream_t st) {
+  int max_rows = 0, max_n = 0;
+  for (int b = 0; b < a.nblocks; ++b) {
+    max_rows = std::max(max_rows, a.n_nodes * a.blk[b].d);
+    max_n = std::max(max_n, a.blk[b].N);
+  }
+  if (max_rows == 0 || max_n == 0) return 0;
+  dim3 grid((max_rows + kGemmBM - 1) / kGemmBM, (max_n + kGemmBN - 1) / kGemmBN, a.nblocks);
+  blocklin_gemm_kernel<<<grid, kGemmThreads, 0, st>>>(a);
+  S7B_LAUNCH_CHECK();
+  return 0;
+}
+
+// Block-diagonal linear over irreps: for each l < n_l:  C_l (+)= A_l * W_l, W_l = [K_l, N_l]
+// stored one after another in `W`.  A blocks: (a_off[l], K = a_K[l]); C blocks: (c_off[l], N = c_N[l]).
+static int irreps_linear(const float* A, int lda, const int* a_off, const int* a_K, float* C, int ldc,
+                         const int* c_off, const int* c_N, int n_l, const float* W, int n_nodes,
+                         bool accumulate, cudaStream_t st) {
+  LinArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A;
+  a.C = C;
+  a.lda = lda;
+  a.ldc = ldc;
+  a.n_nodes = n_nodes;
+  a.accumulate = accumulate ? 1 : 0;
+  a.epilogue = kEpiNone;
+  a.nblocks = 0;
+  size_t woff = 0;
+  for (int l = 0; l < n_l; ++l) {
+    if (a_K[l] == 0 || c_N[l] == 0) continue;
+    LinBlock& b = a.blk[a.nblocks++];
+    b.W = W + woff;
+    b.d = 2 * l + 1;
+    b.K = a_K[l];
+    b.N = c_N[l];
+    b.a_off = a_off[l];
+    b.a_cs = a_K[l];
+    b.c_off = c_off[l];
+    b.c_cs = c_N[l];
+    woff += (size_t)a_K[l] * c_N[l];
+  }
+  return launch_gemm(a, st);
+}
+
+static int dense_gemm(const float* A, int K, float* C, int N, const float* W, int64_t rows, int epilogue,
+                      const float* aux_in, float* aux_out, bool accumulate, cudaStream_t st) {
+  // rows can exceed what a single grid.x covers comfortably; chunk to stay below 2^31 indexing
+  const int64_t chunk = 1 << 22;
+  for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+    const int n = (int)std::min<int64_t>(chunk, rows - r0);
+    LinArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = A + r0 * K;
+    a.C = C + r0 * N;
+    a.aux_in = aux_in ? aux_in + r0 * N : nullptr;
+    a.aux_out = aux_out ? aux_out + r0 * N : nullptr;
+    a.lda = K;
+    a.ldc = N;
+    a.n_nodes = n;
+    a.accumulate = accumulate ? 1 : 0;
+    a.epilogue = epilogue;
+    a.nblocks = 1;
+    a.blk[0] = LinBlock{W, 1, K, N, 0, K, 0, N};
+    if (launch_gemm(a, st)) return 1;
+  }
+  return 0;
+}
+
+static int conv_forward(const LayerCfg& L, int lmax_filter, bool table, ConvArgs a, float* out,
+                        cudaStream_t st) {
+  for (int l1 = 0; l1 < L.n_lx; ++l1)
+    if (launch_conv_fwd(l1, lmax_filter, L.lmax_out, table, a, L.roles[l1], out, st)) return 1;
+  return 0;
+}
+
+}  // namespace s7b
+
+// =========================================================================================
+extern "C" {
+
+const char* s7b_last_error(void) { return g_error.c_str(); }
+int s7b_version(void) { return 1; }
+int64_t s7b_launch_count(int reset) {
+  const int64_t v = g_launches + g_conv_launches;
+  if (reset) { g_launches = 0; g_conv_launches = 0; }
+  return v;
+}
+
+int s7b_engine_create(const S7bModelDesc* d, S7bEngine** out) {
+  if (!d || !out) return fail("null argument");
+  if (d->n_layers < 1 || d->n_layers > S7B_MAX_LAYERS) return fail("n_layers out of range");
+  if (d->lmax_filter < 1 || d->lmax_filter > 3) return fail("lmax_filter must be 1..3");
+  if (d->n_basis < 1 || d->n_basis > 8) return fail("n_basis must be 1..8");
+  S7bEngine* e = new S7bEngine();
+  e->desc = *d;
+  e->layers.resize(d->n_layers);
+  for (int t = 0; t < d->n_layers; ++t) {
+    if (d->n_l[t] < 1 || d->n_l[t] > S7B_MAX_L || d->n_l[t + 1] < 1 || d->n_l[t + 1] > S7B_MAX_L) {
+      delete e;
+      return fail("irreps lmax out of range");
+    }
+    if (build_layer_cfg(e->layers[t], d->muls[t], d->n_l[t], d->muls[t + 1], d->n_l[t + 1], d->lmax_filter)) {
+      delete e;
+      return 1;
+    }
+  }
+  if (e->layers[0].n_lx != 1) {
+    delete e;
+    return fail("the first layer input must be scalars only");
+  }
+  e->ny_stride = (d->lmax_filter == 3) ? 16 : ((d->lmax_filter == 2) ? 8 : 4);
+  const int T = d->n_layers;
+  e->x.resize(T);
+  e->g.resize(T);
+  e->wbuf.resize(T);
+  e->z1.resize(T);
+  e->z2.resize(T);
+  e->h1.resize(T);
+  e->h2.resize(T);
+  memset(&e->radial, 0, sizeof(e->radial));
+  e->radial.cutoff = d->cutoff;
+  e->radial.cutoff_fn = d->cutoff_fn;
+  e->radial.cutoff_on = d->cutoff_on;
+  e->radial.poly_p = d->poly_p;
+  e->radial.n_basis = d->n_basis;
+  e->radial.knots = d->table_knots > 0 ? d->table_knots : 1;
+  e->radial.inv_h = d->table_knots > 0 ? (float)d->table_knots / d->cutoff : 1.0f;
+  *out = e;
+  return 0;
+}
+
+void s7b_engine_destroy(S7bEngine* e) {
+  if (!e) return;
+  for (auto& kv : e->params) kv.second.release();
+  for (auto& L : e->layers)
+    for (auto& kv : L.params) kv.second.release();
+  DevBuf* bufs[] = {&e->rec, &e->Y, &e->rlen, &e->emb, &e->dY_acc, &e->dEdr_acc, &e->demb_acc, &e->fedge,
+                    &e->mid, &e->h, &e->dh, &e->dg, &e->dx, &e->dwbuf, &e->tmpA, &e->tmpB, &e->energy,
+                    &e->atomic_energy, &e->forces, &e->virial, &e->hs_species, &e->hs_rowptr, &e->hs_src,
+                    &e->hs_vec};
+  for (DevBuf* b : bufs) b->release();
+  for (auto* v : {&e->x, &e->g, &e->wbuf, &e->z1, &e->z2, &e->h1, &e->h2})
+    for (auto& b : *v) b.release();
+  delete e;
+}
+
+int s7b_engine_set_param(S7bEngine* e, const char* name, int layer, const float* host, size_t numel) {
+  if (!e || !name || !host) return fail("null argument");
+  const std::string nm(name);
+  if (nm == "bessel") {
+    if ((int)numel != e->desc.n_basis) return fail("bessel: wrong size");
+    for (int b = 0; b < e->desc.n_basis; ++b) e->radial.coeffs[b] = host[b];
+    e->radial_ready = true;
+    return 0;
+  }
+  DevBuf* dst;
+  if (layer < 0) dst = &e->params[nm];
+  else {
+    if (layer >= e->desc.n_layers) return fail("layer out of range");
+    dst = &e->layers[layer].params[nm];
+  }
+  if (dst->ensure(numel * sizeof(float))) return fail("cudaMalloc failed for parameter " + nm);
+  S7B_CUDA_CHECK(cudaMemcpy(dst->p, host, numel * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static const float* lparam(const S7bEngine* e, int t, const char* name) {
+  auto it = e->layers[t].params.find(name);
+  return it == e->layers[t].params.end() ? nullptr : it->second.as<float>();
+}
+static const float* gparam(const S7bEngine* e, const char* name) {
+  auto it = e->params.find(name);
+  return it == e->params.end() ? nullptr : it->second.as<float>();
+}
+
+int s7b_engine_set_graph(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t n_edges,
+                         const int32_t* d_species, const int32_t* d_rowptr, const int32_t* d_src,
+                         const float* d_edge_vec, void* stream) {
+  (void)stream;
+  if (!e) return fail("null engine");
+  if (n_local < 0 || n_nodes < n_local || n_edges < 0) return fail("bad graph sizes");
+  if (n_edges >= ((int64_t)1 << 31)) return fail("more than 2^31-1 edges per GPU are not supported");
+  e->n_nodes = n_nodes;
+  e->n_local = n_local;
+  e->n_edges = n_edges;
+  e->d_species = d_species;
+  e->d_rowptr = d_rowptr;
+  e->d_src = d_src;
+  e->d_edge_vec = d_edge_vec;
+  const bool table = e->desc.table_knots > 0;
+  const size_t E = (size_t)std::max<int64_t>(n_edges, 1), Nn = (size_t)std::max(n_nodes, 1), Nl = (size_t)std::max(n_local, 1);
+  const int T = e->desc.n_layers;
+  int rc = 0;
+  rc |= e->rec.ensure(E * sizeof(int4));
+  rc |= e->Y.ensure(E * e->ny_stride * sizeof(float));
+  rc |= e->rlen.ensure(E * sizeof(float));
+  int max_lx = 0;
+  for (auto& L : e->layers) max_lx = std::max(max_lx, L.n_lx);
+  rc |= e->dY_acc.ensure((size_t)max_lx * E * e->ny_stride * sizeof(float));
+  rc |= e->dEdr_acc.ensure((size_t)max_lx * E * sizeof(float));
+  rc |= e->fedge.ensure(E * 3 * sizeof(float));
+  size_t max_mid = 0, max_h = 0, max_g = 0, max_x = 0, max_W = 0;
+  for (int t = 0; t < T; ++t) {
+    const LayerCfg& L = e->layers[t];
+    rc |= e->x[t].ensure(Nn * L.dim_x * sizeof(float));
+    rc |= e->g[t].ensure(Nl * L.dim_g * sizeof(float));
+    max_mid = std::max(max_mid, (size_t)L.dim_mid);
+    max_h = std::max(max_h, (size_t)L.dim_h);
+    max_g = std::max(max_g, (size_t)L.dim_g);
+    max_x = std::max(max_x, (size_t)L.dim_x);
+    max_W = std::max(max_W, (size_t)L.W);
+    if (!table) {
+      const int h0 = e->desc.radial_hidden[0], h1 = e->desc.radial_hidden[1];
+      rc |= e->wbuf[t].ensure(E * L.W * sizeof(float));
+      rc |= e->z1[t].ensure(E * h0 * sizeof(float));
+      rc |= e->h1[t].ensure(E * h0 * sizeof(float));
+      rc |= e->z2[t].ensure(E * h1 * sizeof(float));
+      rc |= e->h2[t].ensure(E * h1 * sizeof(float));
+    }
+  }
+  if (!table) {
+    rc |= e->emb.ensure(E * e->desc.n_basis * sizeof(float));
+    rc |= e->demb_acc.ensure(E * e->desc.n_basis * sizeof(float));
+    rc |= e->dwbuf.ensure(E * max_W * sizeof(float));
+    const size_t hh = (size_t)std::max(e->desc.radial_hidden[0], e->desc.radial_hidden[1]);
+    rc |= e->tmpA.ensure(E * hh * sizeof(float));
+    rc |= e->tmpB.ensure(E * hh * sizeof(float));
+  }
+  rc |= e->mid.ensure(Nl * max_mid * sizeof(float));
+  rc |= e->h.ensure(Nl * std::max(max_h, max_x) * sizeof(float));
+  rc |= e->dh.ensure(Nl * std::max(max_h, max_x) * sizeof(float));
+  rc |= e->dg.ensure(Nl * max_g * sizeof(float));
+  rc |= e->dx.ensure(Nn * max_x * sizeof(float));
+  rc |= e->energy.ensure(sizeof(double));
+  rc |= e->virial.ensure(6 * sizeof(double));
+  rc |= e->atomic_energy.ensure(Nl * sizeof(float));
+  rc |= e->forces.ensure(Nn * 3 * sizeof(float));
+  if (rc) return fail("cudaMalloc failed while sizing step buffers");
+  return 0;
+}
+
+static ConvArgs make_conv_args(const S7bEngine* e, int t, const float* x) {
+  const LayerCfg& L = e->layers[t];
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rowptr = e->d_rowptr;
+  a.rec = e->rec.as<int4>();
+  a.Y = e->Y.as<float>();
+  a.x = x;
+  a.table = reinterpret_cast<const float4*>(lparam(e, t, "table"));
+  a.w = e->desc.table_knots > 0 ? nullptr : e->wbuf[t].as<float>();
+  a.n_dst = e->n_local;
+  a.dim_x = L.dim_x;
+  a.dim_mid = L.dim_mid;
+  a.w_numel = L.W;
+  a.ny_stride = e->ny_stride;
+  a.inv_h = e->radial.inv_h;
+  return a;
+}
+
+static int grid1d(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  if (g > 148 * 64) g = 148 * 64;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static int require(const void* p, const char* what) {
+  if (p) return 0;
+  return fail(std::string("missing parameter: ") + what);
+}
+
+int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
+  if (!e) return fail("null engine");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int T = e->desc.n_layers;
+  const int Nn = e->n_nodes, Nl = e->n_local;
+  const int64_t E = e->n_edges;
+  const bool table = e->desc.table_knots > 0;
+  const int LF = e->desc.lmax_filter;
+  if (!e->radial_ready) return fail("parameter 'bessel' was not set");
+
+  switch (stage) {
+    case S7B_STAGE_FWD_BEGIN: {
+      if (E > 0) {
+        const int blk = 256;
+        const int grd = (int)((E + blk - 1) / blk);
+        float* emb = table ? nullptr : e->emb.as<float>();
+        if (LF == 1) edge_fwd_kernel<1><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
+        else if (LF == 2) edge_fwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
+        else edge_fwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
+        S7B_LAUNCH_CHECK();
+        int max_lx = 0;
+        for (auto& L : e->layers) max_lx = std::max(max_lx, L.n_lx);
+        S7B_CUDA_CHECK(cudaMemsetAsync(e->dY_acc.p, 0, (size_t)max_lx * E * e->ny_stride * sizeof(float), st));
+        S7B_CUDA_CHECK(cudaMemsetAsync(e->dEdr_acc.p, 0, (size_t)max_lx * E * sizeof(float), st));
+        if (!table) S7B_CUDA_CHECK(cudaMemsetAsync(e->demb_acc.p, 0, (size_t)E * e->desc.n_basis * sizeof(float), st));
+      }
+      const LayerCfg& L0 = e->layers[0];
+      const float* ex = gparam(e, "embed_x0");
+      const float* eg = gparam(e, "embed_g0");
+      if (require(ex, "embed_x0") || require(eg, "embed_g0")) return 1;
+      if (Nn > 0) {
+        gather_rows_kernel<<<grid1d((size_t)Nn * L0.dim_x, 256), 256, 0, st>>>(ex, e->d_species, e->x[0].as<float>(), Nn, L0.dim_x, L0.dim_x);
+        S7B_LAUNCH_CHECK();
+      }
+      if (Nl > 0) {
+        gather_rows_kernel<<<grid1d((size_t)Nl * L0.dim_g, 256), 256, 0, st>>>(eg, e->d_species, e->g[0].as<float>(), Nl, L0.dim_g, L0.dim_g);
+        S7B_LAUNCH_CHECK();
+      }
+      return 0;
+    }
+    case S7B_STAGE_FWD_LAYER: {
+      if (t < 0 || t >= T) return fail("layer out of range");
+      const LayerCfg& L = e->layers[t];
+      if (Nl == 0) return 0;
+      if (!table && E > 0) {
+        // exact radial MLP (convolution.py:121): emb -> h1 -> h2 -> w
+        const float *w0 = lparam(e, t, "mlp0"), *w1 = lparam(e, t, "mlp1"), *w2 = lparam(e, t, "mlp2");
+        if (require(w0, "mlp0") || require(w1, "mlp1") || require(w2, "mlp2")) return 1;
+        const int nb = e->desc.n_basis, h0 = e->desc.radial_hidden[0], h1 = e->desc.radial_hidden[1];
+        if (dense_gemm(e->emb.as<float>(), nb, e->h1[t].as<float>(), h0, w0, E, kEpiSiluStoreZ, nullptr, e->z1[t].as<float>(), false, st)) return 1;
+        if (dense_gemm(e->h1[t].as<float>(), h0, e->h2[t].as<float>(), h1, w1, E, kEpiSiluStoreZ, nullptr, e->z2[t].as<float>(), false, st)) return 1;
+        if (dense_gemm(e->h2[t].as<float>(), h1, e->wbuf[t].as<float>(), L.W, w2, E, kEpiNone, nullptr, nullptr, false, st)) return 1;
+      } else if (table) {
+        if (require(lparam(e, t, "table"), "table")) return 1;
+      }
+      // convolution: gather + tensor product + scatter (raw sums; 1/denominator is folded into si2)
+      ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
+      if (conv_forward(L, LF, table, ca, e->mid.as<float>(), st)) return 1;
+      // self_interaction_2 accumulated onto the self-connection already stored in g[t]
+      const float* si2 = lparam(e, t, "si2");
+      if (require(si2, "si2")) return 1;
+      if (irreps_linear(e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st)) return 1;
+      // gate
+      gate_fwd_kernel<<<grid1d((size_t)Nl * L.dim_h, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->h.as<float>(), Nl);
+      S7B_LAUNCH_CHECK();
+      if (t + 1 < T) {
+        const LayerCfg& N = e->layers[t + 1];
+        const float *si1 = lparam(e, t + 1, "si1"), *sc = lparam(e, t + 1, "sc");
+        if (require(si1, "si1") || require(sc, "sc")) return 1;
+        // self_interaction_1 of the next layer -> local rows of x[t+1]
+        if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st)) return 1;
+        // self_connection_intro of the next layer -> initial value of g[t+1]
+        S7B_CUDA_CHECK(cudaMemsetAsync(e->g[t + 1].p, 0, (size_t)Nl * N.dim_g * sizeof(float), st));
+        const int n_sc = std::min(N.n_lx, N.n_lg);
+        if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->g[t + 1].as<float>(), N.dim_g, N.g_off, N.g_muls, n_sc, sc, Nl, false, st)) return 1;
+      }
+      return 0;
+    }
+    case S7B_STAGE_FWD_END: {
+      const LayerCfg& L = e->layers[T - 1];
+      const float *wr = gparam(e, "readout"), *scale = gparam(e, "scale"), *shift = gparam(e, "shift");
+      if (require(wr, "readout") || require(scale, "scale") || require(shift, "shift")) return 1;
+      S7B_CUDA_CHECK(cudaMemsetAsync(e->energy.p, 0, sizeof(double), st));
+      if (Nl > 0) {
+        const int blk = 256;
+        readout_kernel<<<(Nl * 32 + blk - 1) / blk, blk, 0, st>>>(e->h.as<float>(), wr, scale, shift, e->d_species, Nl, L.dim_h, e->atomic_energy.as<float>(), e->energy.as<double>(), e->dh.as<float>());
+        S7B_LAUNCH_CHECK();
+      }
+      return 0;
+    }
+    case S7B_STAGE_BWD_LAYER_A: {
+      if (t < 0 || t >= T) return fail("layer out of range");
+      const LayerCfg& L = e->layers[t];
+      if (t > 0 && Nn > 0) S7B_CUDA_CHECK(cudaMemsetAsync(e->dx.p, 0, (size_t)Nn * L.dim_x * sizeof(float), st));
+      if (Nl == 0) return 0;
+      gate_bwd_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl);
+      S7B_LAUNCH_CHECK();
+      const float* si2T = lparam(e, t, "si2T");
+      if (require(si2T, "si2T")) return 1;
+      // d(mid) = dg * si2^T
+      if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st)) return 1;
+      if (E > 0) {
+        ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
+        for (int l1 = 0; l1 < L.n_lx; ++l1) {
+          float* dY = e->dY_acc.as<float>() + (size_t)l1 * E * e->ny_stride;
+          float* dEdr = e->dEdr_acc.as<float>() + (size_t)l1 * E;
+          if (launch_conv_bwd(l1, LF, L.lmax_out, table, t > 0, ca, L.roles[l1], e->mid.as<float>(), e->dx.as<float>(), dY, dEdr, table ? nullptr : e->dwbuf.as<float>(), st)) return 1;
+        }
+        if (!table) {
+          // radial MLP backward: dw -> demb (accumulated over layers)
+          const float *w0T = lparam(e, t, "mlp0T"), *w1T = lparam(e, t, "mlp1T"), *w2T = lparam(e, t, "mlp2T");
+          if (require(w0T, "mlp0T") || require(w1T, "mlp1T") || require(w2T, "mlp2T")) return 1;
+          const int nb = e->desc.n_basis, h0 = e->desc.radial_hidden[0], h1 = e->desc.radial_hidden[1];
+          if (dense_gemm(e->dwbuf.as<float>(), L.W, e->tmpA.as<float>(), h1, w2T, E, kEpiMulDsilu, e->z2[t].as<float>(), nullptr, false, st)) return 1;
+          if (dense_gemm(e->tmpA.as<float>(), h1, e->tmpB.as<float>(), h0, w1T, E, kEpiMulDsilu, e->z1[t].as<float>(), nullptr, false, st)) return 1;
+          if (dense_gemm(e->tmpB.as<float>(), h0, e->demb_acc.as<float>(), nb, w0T, E, kEpiNone, nullptr, nullptr, true, st)) return 1;
+        }
+      }
+      return 0;
+    }
+    case S7B_STAGE_BWD_LAYER_B: {
+      if (t <= 0 || t >= T) return fail("BWD_LAYER_B needs 1 <= layer < n_layers");
+      const LayerCfg& L = e->layers[t];
+      if (Nl == 0) return 0;
+      const float *si1T = lparam(e, t, "si1T"), *scT = lparam(e, t, "scT");
+      if (require(si1T, "si1T") || require(scT, "scT")) return 1;
+      // dE/dh(t) = dx(t) * si1^T + dg(t) * sc^T     (h(t) = gate output of layer t-1)
+      if (irreps_linear(e->dx.as<float>(), L.dim_x, L.x_off, L.x_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, L.n_lx, si1T, Nl, false, st)) return 1;
+      const int n_sc = std::min(L.n_lx, L.n_lg);
+      if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, n_sc, scT, Nl, true, st)) return 1;
+      return 0;
+    }
+    case S7B_STAGE_BWD_END: {
+      S7B_CUDA_CHECK(cudaMemsetAsync(e->forces.p, 0, (size_t)std::max(Nn, 1) * 3 * sizeof(float), st));
+      S7B_CUDA_CHECK(cudaMemsetAsync(e->virial.p, 0, 6 * sizeof(double), st));
+      if (E > 0 && Nl > 0) {
+        const int blk = 256;
+        const int grd = (int)((E + blk - 1) / blk);
+        int max_lx = 0;
+        for (auto& L : e->layers) max_lx = std::max(max_lx, L.n_lx);
+        const float* dEdr = table ? e->dEdr_acc.as<float>() : nullptr;
+        const float* demb = table ? nullptr : e->demb_acc.as<float>();
+        if (LF == 1) edge_bwd_kernel<1><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
+        else if (LF == 2) edge_bwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
+        else edge_bwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
+        S7B_LAUNCH_CHECK();
+        force_scatter_kernel<<<(Nl * 32 + blk - 1) / blk, blk, 0, st>>>(e->d_rowptr, e->d_src, e->d_edge_vec, e->fedge.as<float>(), Nl, e->forces.as<float>(), e->virial.as<double>());
+        S7B_LAUNCH_CHECK();
+      }
+      return 0;
+    }
+    default:
+      return fail("unknown stage");
+  }
+}
+
+int s7b_engine_compute(S7bEngine* e, void* stream) {
+  if (!e) return fail("null engine");
+  const int T = e->desc.n_layers;
+  if (s7b_engine_run_stage(e, S7B_STAGE_FWD_BEGIN, 0, stream)) return 1;
+  for (int t = 0; t < T; ++t)
+    if (s7b_engine_run_stage(e, S7B_STAGE_FWD_LAYER, t, stream)) return 1;
+  if (s7b_engine_run_stage(e, S7B_STAGE_FWD_END, 0, stream)) return 1;
+  for (int t = T - 1; t >= 0; --t) {
+    if (s7b_engine_run_stage(e, S7B_STAGE_BWD_LAYER_A, t, stream)) return 1;
+    if (t > 0 && s7b_engine_run_stage(e, S7B_STAGE_BWD_LAYER_B, t, stream)) return 1;
+  }
+  return s7b_engine_run_stage(e, S7B_STAGE_BWD_END, 0, stream);
+}
+
+void* s7b_engine_buffer(S7bEngine* e, const char* name, int layer, size_t* numel) {
+  if (!e || !name) return nullptr;
+  const std::string nm(name);
+  const int T = e->desc.n_layers;
+  size_t n = 0;
+  void* p = nullptr;
+  auto in_range = [&](int t) { return t >= 0 && t < T; };
+  if (nm == "x" && in_range(layer)) { p = e->x[layer].p; n = (size_t)e->n_nodes * e->layers[layer].dim_x; }
+  else if (nm == "gate_in" && in_range(layer)) { p = e->g[layer].p; n = (size_t)e->n_local * e->layers[layer].dim_g; }
+  else if (nm == "weight" && in_range(layer)) { p = e->wbuf[layer].p; n = (size_t)e->n_edges * e->layers[layer].W; }
+  else if (nm == "dx" && in_range(layer)) { p = e->dx.p; n = (size_t)e->n_nodes * e->layers[layer].dim_x; }
+  else if (nm == "mid" && in_range(layer)) { p = e->mid.p; n = (size_t)e->n_local * e->layers[layer].dim_mid; }
+  else if (nm == "h" && in_range(layer)) { p = e->h.p; n = (size_t)e->n_local * e->layers[layer].dim_h; }
+  else if (nm == "dh" && in_range(layer)) { p = e->dh.p; n = (size_t)e->n_local * e->layers[layer].dim_x; }
+  else if (nm == "energy") { p = e->energy.p; n = 1; }
+  else if (nm == "virial") { p = e->virial.p; n = 6; }
+  else if (nm == "atomic_energy") { p = e->atomic_energy.p; n = (size_t)e->n_local; }
+  else if (nm == "forces") { p = e->forces.p; n = (size_t)e->n_nodes * 3; }
+  else if (nm == "edge_force") { p = e->fedge.p; n = (size_t)e->n_edges * 3; }
+  else if (nm == "edge_Y") { p = e->Y.p; n = (size_t)e->n_edges * e->ny_stride; }
+  else if (nm == "edge_rec") { p = e->rec.p; n = (size_t)e->n_edges * 4; }
+  else if (nm == "edge_len") { p = e->rlen.p; n = (size_t)e->n_edges; }
+  else if (nm == "edge_emb") { p = e->emb.p; n = (size_t)e->n_edges * e->desc.n_basis; }
+  else if (nm == "dY_acc") { p = e->dY_acc.p; n = (size_t)e->n_edges * e->ny_stride; }
+  else if (nm == "dEdr_acc") { p = e->dEdr_acc.p; n = (size_t)e->n_edges; }
+  if (numel) *numel = n;
+  return p;
+}
+
+int s7b_engine_compute_host(S7bEngine* e, int32_t n_nodes, int64_t n_edges, const int32_t* species,
+                            const int32_t* edge_centre, const int32_t* edge_neighbour,
+                            const float* edge_vec, double* energy, float* atomic_energy, float* forces,
+                            double* virial, void* stream) {
+  if (!e) return fail("null engine");
+  if (n_nodes < 0 || n_edges < 0) return fail("bad sizes");
+  if (n_nodes > 0 && !species) return fail("null species");
+  if (n_edges > 0 && (!edge_centre || !edge_neighbour || !edge_vec)) return fail("null edge arrays");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // CSR over centres; the caller promises centre-major order (as pair_e3gnn.cpp:136-170 emits)
+  e->host_rowptr.assign((size_t)n_nodes + 1, 0);
+  int prev = 0;
+  for (int64_t k = 0; k < n_edges; ++k) {
+    const int c = edge_centre[k];
+    if (c < prev || c >= n_nodes) return fail("edges must be sorted by centre and centres must be < n_nodes");
+    if (edge_neighbour[k] < 0 || edge_neighbour[k] >= n_nodes) return fail("edge neighbour index out of range");
+    prev = c;
+    e->host_rowptr[(size_t)c + 1]++;
+  }
+  for (int i = 0; i < n_nodes; ++i) e->host_rowptr[(size_t)i + 1] += e->host_rowptr[i];
+  const size_t E = (size_t)std::max<int64_t>(n_edges, 1), N = (size_t)std::max(n_nodes, 1);
+  if (e->hs_species.ensure(N * sizeof(int)) || e->hs_rowptr.ensure((N + 1) * sizeof(int)) ||
+      e->hs_src.ensure(E * sizeof(int)) || e->hs_vec.ensure(E * 3 * sizeof(float)))
+    return fail("cudaMalloc failed for staging buffers");
+  if (n_nodes > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_species.p, species, (size_t)n_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+  S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_rowptr.p, e->host_rowptr.data(), ((size_t)n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (n_edges > 0) {
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_src.p, edge_neighbour, (size_t)n_edges * sizeof(int), cudaMemcpyHostToDevice, st));
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_vec.p, edge_vec, (size_t)n_edges * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  if (s7b_engine_set_graph(e, n_nodes, n_nodes, n_edges, e->hs_species.as<int>(), e->hs_rowptr.as<int>(), e->hs_src.as<int>(), e->hs_vec.as<float>(), stream)) return 1;
+  if (s7b_engine_compute(e, stream)) return 1;
+  if (energy) S7B_CUDA_CHECK(cudaMemcpyAsync(energy, e->energy.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (virial) S7B_CUDA_CHECK(cudaMemcpyAsync(virial, e->virial.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (atomic_energy && n_nodes > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(atomic_energy, e->atomic_energy.p, (size_t)n_nodes * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (forces && n_nodes > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(forces, e->forces.p, (size_t)n_nodes * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  S7B_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- operator-level plug-in -----------------------------------------------------------------
+int s7b_conv_plan_create(int32_t n_l_x, const int32_t* x_muls, int32_t lmax_filter, int32_t lmax_out,
+                         S7bConvPlan** out) {
+  if (!x_muls || !out) return fail("null argument");
+  if (n_l_x < 1 || n_l_x > S7B_MAX_L || lmax_filter < 1 || lmax_filter > 3 || lmax_out < 0 || lmax_out > 3)
+    return fail("irreps out of the supported range (l <= 3)");
+  S7bConvPlan* p = new S7bConvPlan();
+  int out_muls[kMaxL] = {32, 32, 32, 32};   // only lmax_out matters for the path set
+  if (build_layer_cfg(p->cfg, x_muls, n_l_x, out_muls, lmax_out + 1, lmax_filter)) {
+    delete p;
+    return 1;
+  }
+  p->lmax_filter = lmax_filter;
+  p->ny_stride = (lmax_filter == 3) ? 16 : ((lmax_filter == 2) ? 8 : 4);
+  *out = p;
+  return 0;
+}
+
+void s7b_conv_plan_destroy(S7bConvPlan* p) { delete p; }
+
+int s7b_conv_plan_dims(const S7bConvPlan* p, int32_t* dim_x, int32_t* dim_mid, int32_t* weight_numel,
+                       int32_t* n_sh) {
+  if (!p) return fail("null plan");
+  if (dim_x) *dim_x = p->cfg.dim_x;
+  if (dim_mid) *dim_mid = p->cfg.dim_mid;
+  if (weight_numel) *weight_numel = p->cfg.W;
+  if (n_sh) *n_sh = (p->lmax_filter + 1) * (p->lmax_filter + 1);
+  return 0;
+}
+
+}  // extern "C"
+
+namespace s7b {
+
+// rec[e] = {src, 0, 0, 0};  Ypk[e, :] = sh[e, 1:]
+__global__ void conv_pack_kernel(const int* __restrict__ src, const float* __restrict__ sh, int n_sh,
+                                 int ny_stride, int64_t n_edges, int4* __restrict__ rec,
+                                 float* __restrict__ Ypk) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  rec[e] = make_int4(src[e], 0, 0, 0);
+  for (int j = 0; j < ny_stride; ++j) Ypk[e * ny_stride + j] = (j + 1 < n_sh) ? sh[e * n_sh + j + 1] : 0.0f;
+}
+
+// grad_sh[e, 0] = 0; grad_sh[e, j] = sum_parts dY_acc[part, e, j-1]
+__global__ void conv_unpack_grad_kernel(const float* __restrict__ dY_acc, int n_part, int n_sh,
+                                        int ny_stride, int64_t n_edges, float* __restrict__ grad_sh) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  grad_sh[e * n_sh] = 0.0f;
+  for (int j = 1; j < n_sh; ++j) {
+    float s = 0.0f;
+    for (int p = 0; p < n_part; ++p) s += dY_acc[((size_t)p * n_edges + e) * ny_stride + j - 1];
+    grad_sh[e * n_sh + j] = s;
+  }
+}
+
+}  // namespace s7b
+
+extern "C" {
+
+int s7b_conv_forward(const S7bConvPlan* p, const float* x, const float* sh, const float* weight,
+                     const int32_t* rowptr, const int32_t* src, int32_t n_nodes, int32_t n_dst,
+                     int64_t n_edges, float* out, void* stream) {
+  if (!p) return fail("null plan");
+  (void)n_nodes;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const LayerCfg& L = p->cfg;
+  if (n_dst <= 0) return 0;
+  if (n_edges == 0) {   // reference convolution.py:265-268: no launch, zeros out
+    S7B_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)n_dst * L.dim_mid * sizeof(float), st));
+    return 0;
+  }
+  const int n_sh = (p->lmax_filter + 1) * (p->lmax_filter + 1);
+  int4* rec = nullptr;
+  float* Ypk = nullptr;
+  S7B_CUDA_CHECK(cudaMallocAsync((void**)&rec, (size_t)n_edges * sizeof(int4), st));
+  S7B_CUDA_CHECK(cudaMallocAsync((void**)&Ypk, (size_t)n_edges * p->ny_stride * sizeof(float), st));
+  conv_pack_kernel<<<(int)((n_edges + 255) / 256), 256, 0, st>>>(src, sh, n_sh, p->ny_stride, n_edges, rec, Ypk);
+  S7B_LAUNCH_CHECK();
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rowptr = rowptr;
+  a.rec = rec;
+  a.Y = Ypk;
+  a.x = x;
+  a.w = weight;
+  a.n_dst = n_dst;
+  a.dim_x = L.dim_x;
+  a.dim_mid = L.dim_mid;
+  a.w_numel = L.W;
+  a.ny_stride = p->ny_stride;
+  a.inv_h = 1.0f;
+  int rc = conv_forward(L, p->lmax_filter, false, a, out, st);
+  cudaFreeAsync(rec, st);
+  cudaFreeAsync(Ypk, st);
+  return rc;
+}
+
+int s7b_conv_backward(const S7bConvPlan* p, const float* x, const float* sh, const float* weight,
+                      const int32_t* rowptr, const int32_t* src, int32_t n_nodes, int32_t n_dst,
+                      int64_t n_edges, const float* grad_out, float* grad_x, float* grad_sh,
+                      float* grad_weight, void* stream) {
+  if (!p) return fail("null plan");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const LayerCfg& L = p->cfg;
+  const int n_sh = (p->lmax_filter + 1) * (p->lmax_filter + 1);
+  if (n_nodes > 0) S7B_CUDA_CHECK(cudaMemsetAsync(grad_x, 0, (size_t)n_nodes * L.dim_x * sizeof(float), st));
+  if (n_edges == 0 || n_dst <= 0) return 0;
+  int4* rec = nullptr;
+  float *Ypk = nullptr, *dY = nullptr;
+  S7B_CUDA_CHECK(cudaMallocAsync((void**)&rec, (size_t)n_edges * sizeof(int4), st));
+  S7B_CUDA_CHECK(cudaMallocAsync((void**)&Ypk, (size_t)n_edges * p->ny_stride * sizeof(float), st));
+  S7B_CUDA_CHECK(cudaMallocAsync((void**)&dY, (size_t)L.n_lx * n_edges * p->ny_stride * sizeof(float), st));
+  S7B_CUDA_CHECK(cudaMemsetAsync(dY, 0, (size_t)L.n_lx * n_edges * p->ny_stride * sizeof(float), st));
+  conv_pack_kernel<<<(int)((n_edges + 255) / 256), 256, 0, st>>>(src, sh, n_sh, p->ny_stride, n_edges, rec, Ypk);
+  S7B_LAUNCH_CHECK();
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rowptr = rowptr;
+  a.rec = rec;
+  a.Y = Ypk;
+  a.x = x;
+  a.w = weight;
+  a.n_dst = n_dst;
+  a.dim_x = L.dim_x;
+  a.dim_mid = L.dim_mid;
+  a.w_numel = L.W;
+  a.ny_stride = p->ny_stride;
+  a.inv_h = 1.0f;
+  int rc = 0;
+  for (int l1 = 0; l1 < L.n_lx && !rc; ++l1)
+    rc = launch_conv_bwd(l1, p->lmax_filter, L.lmax_out, false, true, a, L.roles[l1], grad_out, grad_x,
+                         dY + (size_t)l1 * n_edges * p->ny_stride, nullptr, grad_weight, st);
+  if (!rc) {
+    conv_unpack_grad_kernel<<<(int)((n_edges + 255) / 256), 256, 0, st>>>(dY, L.n_lx, n_sh, p->ny_stride, n_edges, grad_sh);
+    ++g_launches;
+    if (cudaGetLastError() != cudaSuccess) rc = fail("conv_unpack_grad_kernel launch failed");
+  }
+  cudaFreeAsync(rec, st);
+  cudaFreeAsync(Ypk, st);
+  cudaFreeAsync(dY, st);
+  return rc;
+}
+
+}  // extern "C"
