@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the per-MD-step energy+force hot path (BASELINE.json metric:
+atom-updates/sec per MD step, SevenNet-0, 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU oracle (reference arm)
+
+One "step" = one energy+force evaluation of one periodic Si cell with a fixed neighbour list:
+  N = 1 : BASELINE configs[1], SevenNet-0, Si 10x10x15 = 12 000 atoms, 336 000 edges
+  N > 1 : weak scaling at ~12 500 atoms per GPU (configs[3] at N = 8: Si 25x25x20 = 100 000 atoms),
+          spatial brick decomposition with NCCL ghost exchange (one rank per GPU, torchrun).
+`value` is timed with inputs resident in HBM (CUDA events, L2 flushed between steps); `e2e` is
+the same metric through the host-buffer C-ABI call with pinned host inputs copied in and
+forces/energy copied out inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'atom_updates_per_sec'
+UNIT = 'atom-updates/s'
+CELLS = {1: (10, 10, 15), 2: (25, 25, 5), 4: (25, 25, 10), 8: (25, 25, 20)}
+GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                 '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_system(cells):
+    from sevenn_b200.neighbors import build_graph, diamond_si
+    pos, cell, z = diamond_si(*cells)
+    ei, ev = build_graph(pos, cell, True, 5.0)
+    return pos, cell, z, ei, ev
+
+
+def oracle_step_time(n_atoms_target, threads):
+    """Times the CPU oracle (fp32 torch-CPU) on a bounded Si sample; returns (atoms, seconds)."""
+    import torch
+    from oracle.oracle import Oracle
+    from sevenn_b200.checkpoint import load_weights
+    torch.set_num_threads(threads)
+    meta, arrays = load_weights(os.path.join(ROOT, 'weights', 'sevennet_0.npz'))
+    o = Oracle(meta, arrays, dtype=torch.float32)
+    return o, meta
+
+
+def run_reference(args):
+    """Reference arm: the CPU oracle (this repo's restatement of the reference torch/e3nn path; the
+    reference itself cannot be imported without e3nn) on the box's host cores, bounded sample."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    o, meta = oracle_step_time(0, threads)
+    tm = {int(k): int(v) for k, v in meta['type_map'].items()}
+    # calibrate the sample: largest of 216 / 512 / 1000 atoms whose step stays below ~4 s
+    sample = None
+    for nc in (3, 4, 5):
+        pos, cell, z, ei, ev = make_system((nc, nc, nc))
+        sp = np.array([tm[int(a)] for a in z])
+        t0 = time.perf_counter()
+        o.forward(sp, ei, ev)
+        dt = time.perf_counter() - t0
+        sample = (nc, sp, ei, ev, len(z))
+        if dt * (((nc + 1) / nc) ** 3) > 4.0:
+            break
+    nc, sp, ei, ev, n_atoms = sample
+    for _ in range(max(args.warmup, 1)):
+        o.forward(sp, ei, ev)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        o.forward(sp, ei, ev)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = n_atoms * args.steps / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'gpu_launches': 0,
+        'config': {'workload': f'SevenNet-0 energy+forces, Si {nc}x{nc}x{nc} diamond cells = {n_atoms} atoms, '
+                               f'{ei.shape[1]} edges (bounded CPU sample of the 12 000-atom workload)',
+                   'weights': 'SevenNet-0 (11Jul2024) converted checkpoint'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': f'{n_atoms}-atom Si cell, {args.steps} steps, torch-CPU fp32 oracle'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from sevenn_b200.checkpoint import load_weights
+    from sevenn_b200.engine import B200Engine
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{args.model}.npz'))
+    tm = {int(k): int(v) for k, v in meta['type_map'].items()}
+    cells = CELLS[args.gpus] if args.cells is None else tuple(args.cells)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    sampler = ClockSampler(local_rank)
+    if world == 1:
+        pos, cell, z, ei, ev = make_system(cells)
+        n_atoms, n_edges = len(z), ei.shape[1]
+        species = np.array([tm[int(a)] for a in z], dtype=np.int32)
+        eng = B200Engine(meta, arrays, radial=args.radial, device=local_rank)
+        eng.set_graph(species, ei, ev)
+
+        def step():
+            eng.compute()
+        runner = None
+    else:
+        from sevenn_b200.parallel import DistributedRunner, brick_decompose
+        from sevenn_b200.neighbors import diamond_si
+        pos, cell, z = diamond_si(*cells)
+        n_atoms = len(z)
+        species_all = np.array([tm[int(a)] for a in z], dtype=np.int32)
+        part = brick_decompose(pos, cell, species_all, GRIDS[args.gpus], rank, 5.0)
+        n_edges_local = part['edge_index'].shape[1]
+        eng = B200Engine(meta, arrays, radial=args.radial, device=local_rank)
+        runner = DistributedRunner(eng, part)
+        t = torch.tensor([n_edges_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        n_edges = int(t.item())
+
+        def step():
+            runner.compute()
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    eng.launch_count(reset=True)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        flush.fill_(1)          # evict L2 between timed iterations (untimed)
+        if world > 1:
+            dist.barrier()
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = n_atoms * args.steps / (total_ms * 1e-3)
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) ---------------------------
+    roofline, breakdown = None, None
+    if rank == 0:
+        eng.set_profiling(True)
+        for _ in range(min(args.steps, 10)):
+            flush.fill_(1)
+            step()
+        torch.cuda.synchronize()
+        prof = eng.profile()
+        eng.set_profiling(False)
+        roofline, breakdown = roofline_from_profile(eng, prof, n_edges if world == 1 else n_edges_local, eng.n_local)
+
+    # ---- end to end through the host-buffer entry (N = 1) or the runner's host path (N > 1) -------
+    if world == 1:
+        def pinned(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t, t.numpy()
+        keep = [pinned(species), pinned(ei[0].astype(np.int32)), pinned(ei[1].astype(np.int32)), pinned(ev.astype(np.float32))]
+        h_sp, h_c, h_n, h_v = [k[1] for k in keep]
+        h2d = h_sp.nbytes + 4 * (n_atoms + 1) + h_n.nbytes + h_v.nbytes
+        d2h = 12 * n_atoms + 4 * n_atoms + 8 + 48
+
+        def e2e_step():
+            return eng.compute_host(h_sp, h_c, h_n, h_v)
+    else:
+        h2d, d2h = runner.host_bytes()
+
+        def e2e_step():
+            return runner.compute_host()
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        out = e2e_step()
+    b.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    e2e_ms = torch.tensor([max(a.elapsed_time(b), wall * 1e3)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = n_atoms * args.steps / (float(e2e_ms.item()) * 1e-3)
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {
+                'workload': f'{args.model} energy+forces per MD step, diamond Si {cells[0]}x{cells[1]}x{cells[2]} cells = '
+                            f'{n_atoms} atoms, {n_edges} directed edges, cutoff 5.0 A, positions = lattice + N(0, 0.05 A)',
+                'weights': f'{args.model} converted from the reference checkpoint', 'radial': args.radial,
+                'parallelism': 'single GPU' if world == 1 else f'spatial bricks {GRIDS[args.gpus]} + NCCL ghost exchange',
+                'l2': 'flushed with a 256 MiB write between timed steps',
+                'energy_eV': float(out[0]) if world == 1 else float(out['energy'])},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernel_breakdown_ms': breakdown,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline_from_profile(eng, prof, n_edges, n_dst):
+    """Roofline of the dominant kernel from the engine's CUDA-event profile.  Algorithmic bytes of a
+    convolution launch: per edge the gathered x slice, the cubic radial
+    coefficients of this l1's weight columns, the edge record + harmonics, the dY/dEdr
+    read-modify-write and (backward) the dx reduction; per centre atom the mid-feature slice."""
+    if not prof:
+        return None, None
+    steps = max(c for _, c in prof.values())
+    breakdown = {k: v[0] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+    name = next(iter(breakdown))
+    ms = breakdown[name]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
+    alg = None
+    if name.startswith('conv_'):
+        parts = name.split('.')
+        t, l1 = int(parts[1][1:]), int(parts[2][1:])
+        L = eng.spec.layers[t]
+        mul = L.x_muls[l1]
+        paths = [p for p in L.paths if p.l1 == l1]
+        nacc = sum(2 * p.l3 + 1 for p in paths)
+        ny = eng.spec.n_sh - 1
+        per_edge = 4 * (2 * l1 + 1) * mul + 16 + 4 * ((ny + 3) // 4 * 4)
+        per_edge += (16 if eng.radial == 'table' else 4) * len(paths) * mul
+        per_node = 4 * nacc * mul
+        if name.startswith('conv_bwd'):
+            per_edge += 4 * (2 * l1 + 1) * mul * (1 if t > 0 else 0) + 8 * ((ny + 3) // 4 * 4) + 8
+            if eng.radial != 'table':
+                per_edge += 4 * len(paths) * mul
+        alg = per_edge * n_edges + per_node * n_dst
+    if alg is None:
+        return {'kernel': name, 'ms': ms, 'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s',
+                'frac': None, 'traffic': None, 'peak_source': src}, breakdown
+    achieved = alg / (ms * 1e-3) / 1e9
+    return {'kernel': name, 'ms': ms, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak, 'traffic': None, 'algorithmic_bytes': alg, 'peak_source': src,
+            'note': 'algorithmic bytes include the L2-resident radial-table reads; traffic (ncu dram bytes) is in profiles/'}, breakdown
+
+
+def cpu_baseline():
+    """The oracle (CPU port of the reference torch/e3nn path) on this box's host cores, bounded sample."""
+    import torch
+    threads = os.cpu_count() or 1
+    o, meta = oracle_step_time(0, threads)
+    tm = {int(k): int(v) for k, v in meta['type_map'].items()}
+    pos, cell, z, ei, ev = make_system((4, 4, 4))
+    sp = np.array([tm[int(a)] for a in z])
+    o.forward(sp, ei, ev)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_start < 12.0 and len(times) < 10):
+        t0 = time.perf_counter()
+        o.forward(sp, ei, ev)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {'value': len(z) / best, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'SevenNet-0, {len(z)}-atom Si cell ({ei.shape[1]} edges), best of {len(times)} steps, '
+                      f'torch-CPU fp32 oracle'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--model', default='sevennet_0')
+    ap.add_argument('--radial', default='table', choices=['table', 'mlp'])
+    ap.add_argument('--cells', type=int, nargs=3, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.gpus not in CELLS:
+        raise SystemExit('--gpus must be 1, 2, 4 or 8')
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -108,6 +108,13 @@ S7B_API int s7b_engine_compute_host(S7bEngine* eng, int32_t n_nodes, int64_t n_e
                             const int32_t* edge_neighbour, const float* edge_vec, double* energy,
                             float* atomic_energy, float* forces, double* virial, void* stream);
 
+/* Per-kernel timing with CUDA events recorded on the launching stream around every kernel (or
+ * kernel group) of the stage sequence; labels like "conv_bwd.t2.l1".  Enable, run steps, then read. */
+S7B_API int s7b_engine_set_profiling(S7bEngine* eng, int enable);
+S7B_API int s7b_engine_profile_count(S7bEngine* eng);
+S7B_API int s7b_engine_profile_entry(S7bEngine* eng, int index, char* name, size_t name_len,
+                                     double* total_ms, int64_t* calls);
+
 /* Number of kernels this library launched since the last reset (bench.py's gpu_launches). */
 S7B_API int64_t s7b_launch_count(int reset);
 

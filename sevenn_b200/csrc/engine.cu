@@ -75,6 +75,54 @@ struct DevBuf {
 
 struct PathCfg { int l1, l2, l3, mul, w_off, k_off; };
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline leg).
+struct Profiler {
+  bool enabled = false;
+  struct Rec { std::string label; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  std::map<std::string, std::pair<double, int64_t>> totals;   // label -> (ms, calls)
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void collect() {
+    for (auto& r : recs) {
+      cudaEventSynchronize(r.b);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      auto& t = totals[r.label];
+      t.first += ms;
+      t.second += 1;
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+  void clear() { collect(); totals.clear(); }
+};
+
+struct ProfScope {
+  Profiler* p;
+  cudaStream_t st;
+  cudaEvent_t b;
+  ProfScope(Profiler& prof, cudaStream_t s, const char* what, int t = -1, int l = -1) : p(nullptr), st(s) {
+    if (!prof.enabled) return;
+    p = &prof;
+    char buf[64];
+    if (t >= 0 && l >= 0) snprintf(buf, sizeof(buf), "%s.t%d.l%d", what, t, l);
+    else if (t >= 0) snprintf(buf, sizeof(buf), "%s.t%d", what, t);
+    else snprintf(buf, sizeof(buf), "%s", what);
+    cudaEvent_t a = prof.get();
+    b = prof.get();
+    cudaEventRecord(a, st);
+    prof.recs.push_back({buf, a, b});
+  }
+  ~ProfScope() { if (p) cudaEventRecord(b, st); }
+};
+
 struct LayerCfg {
   int n_lx = 0, n_lg = 0;             // number of l's in x / gate-out irreps
   int x_muls[kMaxL] = {0}, out_muls[kMaxL] = {0}, g_muls[kMaxL] = {0};
@@ -114,6 +162,7 @@ struct S7bEngine {
   // host staging for compute_host
   DevBuf hs_species, hs_rowptr, hs_src, hs_vec;
   std::vector<int> host_rowptr;
+  Profiler prof;
 };
 
 struct S7bConvPlan {
@@ -515,6 +564,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         const int blk = 256;
         const int grd = (int)((E + blk - 1) / blk);
         float* emb = table ? nullptr : e->emb.as<float>();
+        ProfScope ps(e->prof, st, "edge_fwd");
         if (LF == 1) edge_fwd_kernel<1><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
         else if (LF == 2) edge_fwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
         else edge_fwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
@@ -529,6 +579,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       const float* ex = gparam(e, "embed_x0");
       const float* eg = gparam(e, "embed_g0");
       if (require(ex, "embed_x0") || require(eg, "embed_g0")) return 1;
+      ProfScope ps(e->prof, st, "embed_gather");
       if (Nn > 0) {
         gather_rows_kernel<<<grid1d((size_t)Nn * L0.dim_x, 256), 256, 0, st>>>(ex, e->d_species, e->x[0].as<float>(), Nn, L0.dim_x, L0.dim_x);
         S7B_LAUNCH_CHECK();
@@ -548,6 +599,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         const float *w0 = lparam(e, t, "mlp0"), *w1 = lparam(e, t, "mlp1"), *w2 = lparam(e, t, "mlp2");
         if (require(w0, "mlp0") || require(w1, "mlp1") || require(w2, "mlp2")) return 1;
         const int nb = e->desc.n_basis, h0 = e->desc.radial_hidden[0], h1 = e->desc.radial_hidden[1];
+        ProfScope ps(e->prof, st, "radial_mlp_fwd", t);
         if (dense_gemm(e->emb.as<float>(), nb, e->h1[t].as<float>(), h0, w0, E, kEpiSiluStoreZ, nullptr, e->z1[t].as<float>(), false, st)) return 1;
         if (dense_gemm(e->h1[t].as<float>(), h0, e->h2[t].as<float>(), h1, w1, E, kEpiSiluStoreZ, nullptr, e->z2[t].as<float>(), false, st)) return 1;
         if (dense_gemm(e->h2[t].as<float>(), h1, e->wbuf[t].as<float>(), L.W, w2, E, kEpiNone, nullptr, nullptr, false, st)) return 1;
@@ -556,18 +608,28 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       }
       // convolution: gather + tensor product + scatter (raw sums; 1/denominator is folded into si2)
       ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
-      if (conv_forward(L, LF, table, ca, e->mid.as<float>(), st)) return 1;
+      for (int l1 = 0; l1 < L.n_lx; ++l1) {
+        ProfScope ps(e->prof, st, "conv_fwd", t, l1);
+        if (launch_conv_fwd(l1, LF, L.lmax_out, table, ca, L.roles[l1], e->mid.as<float>(), st)) return 1;
+      }
       // self_interaction_2 accumulated onto the self-connection already stored in g[t]
       const float* si2 = lparam(e, t, "si2");
       if (require(si2, "si2")) return 1;
-      if (irreps_linear(e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st)) return 1;
+      {
+        ProfScope ps(e->prof, st, "si2_gemm", t);
+        if (irreps_linear(e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st)) return 1;
+      }
       // gate
-      gate_fwd_kernel<<<grid1d((size_t)Nl * L.dim_h, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->h.as<float>(), Nl);
-      S7B_LAUNCH_CHECK();
+      {
+        ProfScope ps(e->prof, st, "gate_fwd", t);
+        gate_fwd_kernel<<<grid1d((size_t)Nl * L.dim_h, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->h.as<float>(), Nl);
+        S7B_LAUNCH_CHECK();
+      }
       if (t + 1 < T) {
         const LayerCfg& N = e->layers[t + 1];
         const float *si1 = lparam(e, t + 1, "si1"), *sc = lparam(e, t + 1, "sc");
         if (require(si1, "si1") || require(sc, "sc")) return 1;
+        ProfScope ps(e->prof, st, "si1_sc_gemm", t + 1);
         // self_interaction_1 of the next layer -> local rows of x[t+1]
         if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st)) return 1;
         // self_connection_intro of the next layer -> initial value of g[t+1]
@@ -584,6 +646,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       S7B_CUDA_CHECK(cudaMemsetAsync(e->energy.p, 0, sizeof(double), st));
       if (Nl > 0) {
         const int blk = 256;
+        ProfScope ps(e->prof, st, "readout");
         readout_kernel<<<(Nl * 32 + blk - 1) / blk, blk, 0, st>>>(e->h.as<float>(), wr, scale, shift, e->d_species, Nl, L.dim_h, e->atomic_energy.as<float>(), e->energy.as<double>(), e->dh.as<float>());
         S7B_LAUNCH_CHECK();
       }
@@ -594,17 +657,24 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       const LayerCfg& L = e->layers[t];
       if (t > 0 && Nn > 0) S7B_CUDA_CHECK(cudaMemsetAsync(e->dx.p, 0, (size_t)Nn * L.dim_x * sizeof(float), st));
       if (Nl == 0) return 0;
-      gate_bwd_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl);
-      S7B_LAUNCH_CHECK();
+      {
+        ProfScope ps(e->prof, st, "gate_bwd", t);
+        gate_bwd_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl);
+        S7B_LAUNCH_CHECK();
+      }
       const float* si2T = lparam(e, t, "si2T");
       if (require(si2T, "si2T")) return 1;
       // d(mid) = dg * si2^T
-      if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st)) return 1;
+      {
+        ProfScope ps(e->prof, st, "si2T_gemm", t);
+        if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st)) return 1;
+      }
       if (E > 0) {
         ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
         for (int l1 = 0; l1 < L.n_lx; ++l1) {
           float* dY = e->dY_acc.as<float>() + (size_t)l1 * E * e->ny_stride;
           float* dEdr = e->dEdr_acc.as<float>() + (size_t)l1 * E;
+          ProfScope ps(e->prof, st, "conv_bwd", t, l1);
           if (launch_conv_bwd(l1, LF, L.lmax_out, table, t > 0, ca, L.roles[l1], e->mid.as<float>(), e->dx.as<float>(), dY, dEdr, table ? nullptr : e->dwbuf.as<float>(), st)) return 1;
         }
         if (!table) {
@@ -612,6 +682,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
           const float *w0T = lparam(e, t, "mlp0T"), *w1T = lparam(e, t, "mlp1T"), *w2T = lparam(e, t, "mlp2T");
           if (require(w0T, "mlp0T") || require(w1T, "mlp1T") || require(w2T, "mlp2T")) return 1;
           const int nb = e->desc.n_basis, h0 = e->desc.radial_hidden[0], h1 = e->desc.radial_hidden[1];
+          ProfScope ps(e->prof, st, "radial_mlp_bwd", t);
           if (dense_gemm(e->dwbuf.as<float>(), L.W, e->tmpA.as<float>(), h1, w2T, E, kEpiMulDsilu, e->z2[t].as<float>(), nullptr, false, st)) return 1;
           if (dense_gemm(e->tmpA.as<float>(), h1, e->tmpB.as<float>(), h0, w1T, E, kEpiMulDsilu, e->z1[t].as<float>(), nullptr, false, st)) return 1;
           if (dense_gemm(e->tmpB.as<float>(), h0, e->demb_acc.as<float>(), nb, w0T, E, kEpiNone, nullptr, nullptr, true, st)) return 1;
@@ -626,6 +697,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       const float *si1T = lparam(e, t, "si1T"), *scT = lparam(e, t, "scT");
       if (require(si1T, "si1T") || require(scT, "scT")) return 1;
       // dE/dh(t) = dx(t) * si1^T + dg(t) * sc^T     (h(t) = gate output of layer t-1)
+      ProfScope ps(e->prof, st, "si1T_scT_gemm", t);
       if (irreps_linear(e->dx.as<float>(), L.dim_x, L.x_off, L.x_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, L.n_lx, si1T, Nl, false, st)) return 1;
       const int n_sc = std::min(L.n_lx, L.n_lg);
       if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, n_sc, scT, Nl, true, st)) return 1;
@@ -641,6 +713,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         for (auto& L : e->layers) max_lx = std::max(max_lx, L.n_lx);
         const float* dEdr = table ? e->dEdr_acc.as<float>() : nullptr;
         const float* demb = table ? nullptr : e->demb_acc.as<float>();
+        ProfScope ps(e->prof, st, "edge_bwd_force_scatter");
         if (LF == 1) edge_bwd_kernel<1><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
         else if (LF == 2) edge_bwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
         else edge_bwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
@@ -667,6 +740,32 @@ int s7b_engine_compute(S7bEngine* e, void* stream) {
     if (t > 0 && s7b_engine_run_stage(e, S7B_STAGE_BWD_LAYER_B, t, stream)) return 1;
   }
   return s7b_engine_run_stage(e, S7B_STAGE_BWD_END, 0, stream);
+}
+
+int s7b_engine_set_profiling(S7bEngine* e, int enable) {
+  if (!e) return fail("null engine");
+  e->prof.clear();
+  e->prof.enabled = enable != 0;
+  return 0;
+}
+
+int s7b_engine_profile_count(S7bEngine* e) {
+  if (!e) return 0;
+  e->prof.collect();
+  return (int)e->prof.totals.size();
+}
+
+int s7b_engine_profile_entry(S7bEngine* e, int index, char* name, size_t name_len, double* total_ms,
+                             int64_t* calls) {
+  if (!e) return fail("null engine");
+  e->prof.collect();
+  if (index < 0 || index >= (int)e->prof.totals.size()) return fail("profile index out of range");
+  auto it = e->prof.totals.begin();
+  std::advance(it, index);
+  if (name && name_len > 0) snprintf(name, name_len, "%s", it->first.c_str());
+  if (total_ms) *total_ms = it->second.first;
+  if (calls) *calls = it->second.second;
+  return 0;
 }
 
 void* s7b_engine_buffer(S7bEngine* e, const char* name, int layer, size_t* numel) {

@@ -48,7 +48,8 @@ class S7bModelDesc(ctypes.Structure):
 EXPORTS = [
     's7b_last_error', 's7b_version', 's7b_engine_create', 's7b_engine_destroy',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
-    's7b_engine_buffer', 's7b_engine_compute_host', 's7b_launch_count', 's7b_conv_plan_create',
+    's7b_engine_buffer', 's7b_engine_compute_host', 's7b_launch_count', 's7b_engine_set_profiling',
+    's7b_engine_profile_count', 's7b_engine_profile_entry', 's7b_conv_plan_create',
     's7b_conv_plan_destroy', 's7b_conv_plan_dims', 's7b_conv_forward', 's7b_conv_backward',
 ]
 
@@ -75,6 +76,10 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_engine_buffer.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(sz)]
     lib.s7b_engine_buffer.restype = vp
     lib.s7b_engine_compute_host.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.s7b_engine_set_profiling.argtypes = [vp, ctypes.c_int]
+    lib.s7b_engine_profile_count.argtypes = [vp]
+    lib.s7b_engine_profile_entry.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, sz,
+                                             ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.s7b_launch_count.argtypes = [ctypes.c_int]
     lib.s7b_launch_count.restype = i64
     lib.s7b_conv_plan_create.argtypes = [i32, ctypes.POINTER(i32), i32, i32, ctypes.POINTER(vp)]
@@ -364,6 +369,19 @@ class B200Engine:
         self.n_nodes = self.n_local = n
         self.n_edges = E
         return float(energy[0]), ae, forces, virial
+
+    def set_profiling(self, enable: bool):
+        check(self.lib.s7b_engine_set_profiling(self._h, 1 if enable else 0))
+
+    def profile(self) -> dict:
+        """{label: (total_ms, calls)} accumulated since set_profiling(True)."""
+        out = {}
+        for i in range(self.lib.s7b_engine_profile_count(self._h)):
+            name = ctypes.create_string_buffer(96)
+            ms, calls = ctypes.c_double(), ctypes.c_int64()
+            check(self.lib.s7b_engine_profile_entry(self._h, i, name, 96, ctypes.byref(ms), ctypes.byref(calls)))
+            out[name.value.decode()] = (ms.value, calls.value)
+        return out
 
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.s7b_launch_count(1 if reset else 0))
