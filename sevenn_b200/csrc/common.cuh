@@ -11,7 +11,7 @@
 namespace s7b {
 
 constexpr float kSiluNorm = 1.6791767923989418f;   // e3nn normalize2mom(silu), see spec.py
-constexpr int kMaxPaths = 10;                      // l1 = 3, lmax 3 has 10 paths
+constexpr int kMaxPaths = 12;                      // l1 = 2 with lmax 3 has 11 paths
 constexpr int kMaxL = 4;                           // l = 0..3
 
 // y = c * silu(z)

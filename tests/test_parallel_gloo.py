@@ -1,0 +1,177 @@
+"""CPU tests of the multi-rank path (world_size 2 and 4, gloo): brick decomposition, ghost maps
+and the stage/exchange protocol of sevenn_b200.parallel.DistributedRunner, driven with a small
+CPU stand-in for the CUDA engine that has the same stage interface (a linear-plus-tanh message
+passing model whose serial result is the oracle for the distributed one)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sevenn_b200.engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B, STAGE_FWD_BEGIN,
+                                STAGE_FWD_END, STAGE_FWD_LAYER)
+from sevenn_b200.neighbors import build_graph, diamond_si, rocksalt_nacl
+from sevenn_b200.parallel import DistributedRunner, brick_decompose
+
+
+class _L:
+    def __init__(self, d):
+        self.dim_x = d
+
+
+class _Spec:
+    def __init__(self, n_layers, d):
+        self.n_layers = n_layers
+        self.layers = [_L(d) for _ in range(n_layers)]
+
+
+class FakeEngine:
+    """Same stage protocol as B200Engine, trivial physics:
+       x_0 = (species+1); a_t[i] = sum_{e->i} |v_e| x_t[src_e]; h = tanh(a); x_{t+1} = c_t h; E = sum h_T."""
+    D, T = 4, 3
+
+    def __init__(self):
+        self.spec = _Spec(self.T, self.D)
+        self.device = torch.device('cpu')
+        self.coef = [0.3, 0.2, 0.1]
+
+    def set_graph(self, species, edge_index, edge_vec, n_local=None):
+        self.species = torch.as_tensor(species).double()
+        ei = torch.as_tensor(edge_index).long()
+        self.dst, self.src = ei[0], ei[1]
+        self.vec = torch.as_tensor(edge_vec).double()
+        self.n_nodes = len(self.species)
+        self.n_local = self.n_nodes if n_local is None else n_local
+        self.w = self.vec.norm(dim=1)
+        self.x = [torch.zeros(self.n_nodes, self.D, dtype=torch.float64) for _ in range(self.T)]
+        self.a = [None] * self.T
+        self.dx = torch.zeros(self.n_nodes, self.D, dtype=torch.float64)
+        self.forces = torch.zeros(self.n_nodes, 3, dtype=torch.float64)
+        self.energy = torch.zeros(1, dtype=torch.float64)
+        self.virial = torch.zeros(6, dtype=torch.float64)
+        self.dEdw = torch.zeros(len(self.w), dtype=torch.float64)
+
+    def buffer(self, name, t=0, dtype='f4', shape=None):
+        return {'x': lambda: self.x[t], 'dx': lambda: self.dx, 'forces': lambda: self.forces,
+                'energy': lambda: self.energy, 'virial': lambda: self.virial,
+                'atomic_energy': lambda: torch.zeros(self.n_local)}[name]()
+
+    def run_stage(self, stage, t=0):
+        nl = self.n_local
+        if stage == STAGE_FWD_BEGIN:
+            self.x[0][:] = (self.species + 1.0)[:, None]
+            self.dEdw.zero_()
+        elif stage == STAGE_FWD_LAYER:
+            a = torch.zeros(nl, self.D, dtype=torch.float64).index_add_(0, self.dst, self.w[:, None] * self.x[t][self.src])
+            self.a[t] = a
+            self.h = torch.tanh(a)
+            if t + 1 < self.T:
+                self.x[t + 1][:nl] = self.coef[t] * self.h
+        elif stage == STAGE_FWD_END:
+            self.energy[0] = self.h.sum()
+            self.dh = torch.ones(nl, self.D, dtype=torch.float64)
+        elif stage == STAGE_BWD_LAYER_A:
+            da = self.dh * (1 - torch.tanh(self.a[t]) ** 2)
+            self.dEdw += (da[self.dst] * self.x[t][self.src]).sum(1)
+            self.dx.zero_()
+            if t > 0:
+                self.dx.index_add_(0, self.src, self.w[:, None] * da[self.dst])
+        elif stage == STAGE_BWD_LAYER_B:
+            self.dh = self.coef[t - 1] * self.dx[:nl]
+        elif stage == STAGE_BWD_END:
+            f = self.dEdw[:, None] * self.vec / self.w[:, None]
+            self.forces.zero_()
+            self.forces.index_add_(0, self.dst, f)
+            self.forces.index_add_(0, self.src, -f)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _system(kind):
+    if kind == 'si':
+        pos, cell, z = diamond_si(3, 2, 2, seed=4)
+    else:
+        pos, cell, z = rocksalt_nacl(2, 2, 2, sigma=0.08, seed=7)
+    species = (z == z.min()).astype(np.int32)
+    return pos, cell, species
+
+
+def _worker(rank, world, port, grid, kind, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        pos, cell, species = _system(kind)
+        part = brick_decompose(pos, cell, species, grid, rank, 5.0)
+        eng = FakeEngine()
+        run = DistributedRunner(eng, part)
+        run.compute()
+        q.put((rank, part['global_ids'][:part['n_local']], eng.forces[:part['n_local']].numpy().copy(),
+               float(eng.energy[0]), part['edge_index'].shape[1], part['n_nodes'] - part['n_local']))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,grid,kind', [(2, (2, 1, 1), 'si'), (2, (1, 1, 2), 'nacl'), (4, (2, 2, 1), 'si')])
+def test_distributed_protocol_matches_serial(world, grid, kind):
+    pos, cell, species = _system(kind)
+    ei, ev = build_graph(pos, cell, True, 5.0)
+    ser = FakeEngine()
+    ser.set_graph(species, ei, ev)
+    for st, ts in [(STAGE_FWD_BEGIN, [0]), (STAGE_FWD_LAYER, range(ser.T)), (STAGE_FWD_END, [0])]:
+        for t in ts:
+            ser.run_stage(st, t)
+    for t in range(ser.T - 1, -1, -1):
+        ser.run_stage(STAGE_BWD_LAYER_A, t)
+        if t > 0:
+            ser.run_stage(STAGE_BWD_LAYER_B, t)
+    ser.run_stage(STAGE_BWD_END)
+
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    forces = np.zeros((len(pos), 3))
+    seen = np.zeros(len(pos), dtype=int)
+    n_edges = 0
+    for rank, gids, f, energy, e_loc, n_ghost in res:
+        forces[gids] = f
+        seen[gids] += 1
+        n_edges += e_loc
+        assert abs(energy - float(ser.energy[0])) < 1e-9 * abs(float(ser.energy[0]))   # all-reduced
+        assert n_ghost > 0
+    assert (seen == 1).all()                       # every atom owned exactly once
+    assert n_edges == ei.shape[1]                  # every directed edge appears on exactly one rank
+    assert np.allclose(forces, ser.forces.numpy(), atol=1e-9)
+
+
+def test_brick_decompose_invariants():
+    pos, cell, species = _system('si')
+    ei, ev = build_graph(pos, cell, True, 5.0)
+    parts = [brick_decompose(pos, cell, species, (2, 1, 1), r, 5.0) for r in range(2)]
+    assert sum(p['n_local'] for p in parts) == len(pos)
+    for r, p in enumerate(parts):
+        nl = p['n_local']
+        assert (np.diff(p['edge_index'][0]) >= 0).all() and p['edge_index'][0].max() < nl
+        assert (np.diff(p['ghost_owner']) >= 0).all() and (p['ghost_owner'] != r).all()
+        gids = p['global_ids']
+        assert len(np.unique(gids)) == len(gids)
+        g_edges = {(int(gids[a]), int(gids[b]), tuple(np.round(v, 6))) for a, b, v in zip(p['edge_index'][0], p['edge_index'][1], p['edge_vec'])}
+        mask = np.isin(ei[0], gids[:nl])
+        ref = {(int(a), int(b), tuple(np.round(v, 6))) for a, b, v in zip(ei[0][mask], ei[1][mask], ev[mask])}
+        assert g_edges == ref

@@ -1,0 +1,79 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the brick-decomposed, NCCL-exchanged
+evaluation must reproduce the single-GPU engine and the CPU oracle on the same system."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import model_weights, oracle, species_of
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, grid, model, q):
+    import torch
+    import torch.distributed as dist
+    from sevenn_b200.engine import B200Engine
+    from sevenn_b200.neighbors import diamond_si
+    from sevenn_b200.parallel import DistributedRunner, brick_decompose
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        meta, arrays = model_weights(model)
+        pos, cell, z = diamond_si(4, 3, 3, seed=2)
+        part = brick_decompose(pos, cell, species_of(meta, z), grid, rank, 5.0)
+        run = DistributedRunner(B200Engine(meta, arrays, device=rank), part)
+        run.compute()
+        torch.cuda.synchronize()
+        r = run.results()
+        h = run.compute_host()
+        q.put((rank, r['global_ids'], r['forces'].cpu().numpy(), float(r['energy'].cpu()[0]),
+               r['atomic_energy'].cpu().numpy(), r['virial'].cpu().numpy(), h['energy'], h['forces'].copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,grid,model', [(2, (2, 1, 1), 'sevennet_0'), (2, (1, 2, 1), 'sevennet_l3i5'),
+                                              (4, (2, 2, 1), 'sevennet_0'), (8, (2, 2, 2), 'sevennet_0')])
+def test_multi_gpu_matches_oracle(world, grid, model):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    from sevenn_b200.neighbors import build_graph, diamond_si
+    meta, _ = model_weights(model)
+    pos, cell, z = diamond_si(4, 3, 3, seed=2)
+    ei, ev = build_graph(pos, cell, True, 5.0)
+    ref = oracle(model).forward(species_of(meta, z), ei, ev, volume=abs(np.linalg.det(cell)))
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, grid, model, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    forces = np.zeros((len(pos), 3))
+    forces_h = np.zeros((len(pos), 3))
+    ae = np.zeros(len(pos))
+    for rank, gids, f, energy, a, virial, e_h, f_h in res:
+        forces[gids], forces_h[gids], ae[gids] = f, f_h, a
+        assert abs(energy - float(ref['energy'])) < 1e-4
+        assert abs(e_h - energy) < 1e-6
+        assert np.allclose(virial, ref['virial'].numpy(), atol=1e-3, rtol=1e-5)
+    assert np.allclose(forces, ref['forces'].numpy(), atol=5e-5)
+    assert np.allclose(forces_h, forces, atol=5e-6)
+    assert np.allclose(ae, ref['atomic_energy'].numpy(), atol=2e-5)
