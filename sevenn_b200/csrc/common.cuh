@@ -4,9 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 
-#ifndef S7B_HD
-#define S7B_HD __host__ __device__ __forceinline__
-#endif
+#include "vec_ops.cuh"
 
 namespace s7b {
 
@@ -40,7 +38,7 @@ struct ConvArgs {
   const int4* rec;            // [E] {src, table interval, frac bits, 0}
   const float* Y;             // [E, ny_stride]  Y_1 .. Y_{NY-1} (Y_0 = 1 implicit), zero padded
   const float* x;             // [n_nodes, dim_x]
-  const float4* table;        // [knots, W] cubic coefficients per (interval, weight column)
+  const float4* table;        // [knots, W/2, 2] float4: {a0e,a0o,a1e,a1o}, {a2e,a2o,a3e,a3o} per channel pair
   const float* w;             // [E, W] stored weights (operator boundary / exact-MLP mode)
   int n_dst;
   int dim_x, dim_mid, w_numel, ny_stride;

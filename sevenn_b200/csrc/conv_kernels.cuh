@@ -7,13 +7,15 @@
 // and their autograd backward (sevenn/nn/force_output.py:177-182) with one forward and one
 // backward kernel per l1 "kind" (see csrc/gen_kernels.py).
 //
-// Mapping: one warp owns one destination atom n and one l1 block; lane <-> channel u (NCH
-// channels per lane, 32 apart), so every global access is a 128-byte contiguous segment in the
-// component-major ("cm") layout.  The edge loop runs over the CSR row of n; the accumulators
-// for all paths of the kind stay in registers and are written once -- no atomics in the forward.
-// The radial weights w_p,u(r) come either from a cubic-Hermite table indexed by the edge
-// length (TABLE = true; L2-resident, [knots][W] float4) or from a stored [E, W] array
-// (TABLE = false; the reference's plug-in boundary, where the radial MLP stays outside).
+// Mapping: a group of LPN lanes (32 = a warp, or 16 = half a warp for 32-channel irreps) owns one
+// destination atom n and one l1 block.  Every lane carries NV channel PAIRS (channels 2*lane,
+// 2*lane+1, then +2*LPN): all per-channel arithmetic is issued as Blackwell packed-FP32
+// instructions (FFMA2/FMUL2, csrc/vec_ops.cuh), every global access of a group is one contiguous
+// 8-byte-per-lane segment of the component-major ("cm") layout, and the node accumulators of all
+// paths stay in registers over the whole CSR row -- no atomics in the forward.
+// The radial weights w_p,u(r) come either from a cubic-Hermite table indexed by the edge length
+// (TABLE: L2-resident, [knots][W/2] x {a0,a1 | a2,a3} x {even,odd channel}) or from a stored [E, W]
+// array (!TABLE: the reference's plug-in boundary, where the radial MLP stays outside).
 #pragma once
 #include "common.cuh"
 #include "generated/tp_kinds.cuh"
@@ -22,15 +24,15 @@ namespace s7b {
 
 constexpr int kConvWarpsPerBlock = 4;
 
-// Sum M values (M = 8 or 16) over the 32 lanes with M-1+log2(32/M) shuffles instead of 5*M.
-// On return v[0] of lane L holds the total of value index (L >> (5 - log2 M)) & (M-1).
-template <int M>
-__device__ __forceinline__ void warp_reduce_multi(float (&v)[M], int lane) {
-  static_assert(M == 8 || M == 16, "M must be 8 or 16");
-  int off = 16;
+// Sum M values (M = 8 or 16) over the LPN lanes of a group with ~M-1+log2(LPN/M) shuffles instead
+// of M*log2(LPN).  On return v[0] of group-lane sl holds the total of value (sl / (LPN/M)) % M.
+template <int M, int LPN>
+__device__ __forceinline__ void group_reduce_multi(float (&v)[M], int sl) {
+  static_assert((M == 8 || M == 16) && (LPN == 16 || LPN == 32) && M <= LPN, "unsupported reduction shape");
+  int off = LPN / 2;
 #pragma unroll
   for (int m = M / 2; m >= 1; m >>= 1, off >>= 1) {
-    const bool up = (lane & off) != 0;
+    const bool up = (sl & off) != 0;
 #pragma unroll
     for (int j = 0; j < m; ++j) {
       const float send = up ? v[j] : v[j + m];
@@ -42,19 +44,20 @@ __device__ __forceinline__ void warp_reduce_multi(float (&v)[M], int lane) {
   for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+template <int LPN>
+__device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  for (int off = LPN / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
   return v;
 }
 
 template <class Kind>
 __device__ __forceinline__ void load_Y(const float* __restrict__ Yrow, float (&Y)[Kind::NY]) {
   Y[0] = 1.0f;
-  constexpr int NV = (Kind::NY - 1 + 3) / 4;
+  constexpr int NQ = (Kind::NY - 1 + 3) / 4;
   const float4* p = reinterpret_cast<const float4*>(Yrow);
 #pragma unroll
-  for (int q = 0; q < NV; ++q) {
+  for (int q = 0; q < NQ; ++q) {
     const float4 v = __ldg(p + q);
     if (4 * q + 1 < Kind::NY) Y[4 * q + 1] = v.x;
     if (4 * q + 2 < Kind::NY) Y[4 * q + 2] = v.y;
@@ -63,59 +66,88 @@ __device__ __forceinline__ void load_Y(const float* __restrict__ Yrow, float (&Y
   }
 }
 
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+// Which node / channel pair this lane works on.
+template <int NV, int LPN>
+struct LaneMap {
+  int n, sl, uc0, e0, len, nmax;
+  bool node_ok;
+  __device__ __forceinline__ LaneMap(const ConvArgs& a) {
+    constexpr int GPW = 32 / LPN;
+    const int lane = threadIdx.x & 31;
+    sl = lane % LPN;
+    n = (blockIdx.x * kConvWarpsPerBlock + (threadIdx.x >> 5)) * GPW + lane / LPN;
+    node_ok = n < a.n_dst;
+    uc0 = blockIdx.y * (2 * LPN * NV) + 2 * sl;
+    e0 = 0;
+    len = 0;
+    if (node_ok) {
+      e0 = __ldg(a.rowptr + n);
+      len = __ldg(a.rowptr + n + 1) - e0;
+    }
+    nmax = len;
+    if (GPW > 1) nmax = max(len, __shfl_xor_sync(0xffffffffu, len, 16));
+  }
+};
+
 // ------------------------------------------------------------------------------------------
 // forward:  out[n, path block] = sum_{e in row n} w_e * CG(x[src_e], Y_e)
-// grid = (ceil(n_dst / kConvWarpsPerBlock), mul / (32 * NCH)), block = 32 * kConvWarpsPerBlock
+// grid = (ceil(n_dst / (kConvWarpsPerBlock * 32/LPN)), mul / (2*LPN*NV)), block = 32*kConvWarpsPerBlock
 // ------------------------------------------------------------------------------------------
-template <class Kind, int NCH, bool TABLE>
+template <class Kind, int NV, int LPN, bool TABLE>
 __global__ void __launch_bounds__(32 * kConvWarpsPerBlock)
 conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) {
-  const int n = blockIdx.x * kConvWarpsPerBlock + (threadIdx.x >> 5);
-  if (n >= a.n_dst) return;
-  const int lane = threadIdx.x & 31;
-  const int u0 = blockIdx.y * (32 * NCH) + lane;
-  const int e0 = __ldg(a.rowptr + n), e1 = __ldg(a.rowptr + n + 1);
+  const LaneMap<NV, LPN> m(a);
+  if (m.nmax == 0 && !m.node_ok) return;      // whole warp beyond the last node (uniform)
 
-  float acc[NCH][Kind::NACC];
+  V2 acc[NV][Kind::NACC];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+  for (int c = 0; c < NV; ++c)
 #pragma unroll
-    for (int q = 0; q < Kind::NACC; ++q) acc[c][q] = 0.0f;
+    for (int q = 0; q < Kind::NACC; ++q) acc[c][q] = splat2(0.0f);
 
-  for (int e = e0; e < e1; ++e) {
+  for (int it = 0; it < m.nmax; ++it) {
+    const bool valid = (LPN == 32) || (it < m.len);
+    const int e = valid ? m.e0 + it : 0;
     const int4 rec = __ldg(a.rec + e);
     float Y[Kind::NY];
     load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y);
     const float* __restrict__ xrow = a.x + (size_t)rec.x * a.dim_x + role.x_off;
     const float tt = __int_as_float(rec.z);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int u = u0 + 32 * c;
-      float x[Kind::D1], w[Kind::NPATH];
+    for (int c = 0; c < NV; ++c) {
+      const int u = m.uc0 + 2 * LPN * c;
+      V2 x[Kind::D1], w[Kind::NPATH];
 #pragma unroll
-      for (int i = 0; i < Kind::D1; ++i) x[i] = __ldg(xrow + i * role.mul + u);
+      for (int i = 0; i < Kind::D1; ++i) x[i] = ldg2(xrow + i * role.mul + u);
 #pragma unroll
       for (int p = 0; p < Kind::NPATH; ++p) {
         if (TABLE) {
-          const float4 cf = __ldg(a.table + (size_t)rec.y * a.w_numel + role.w_off[p] + u);
-          w[p] = fmaf(tt, fmaf(tt, fmaf(tt, cf.w, cf.z), cf.y), cf.x);
+          const float4* cp = a.table + ((size_t)rec.y * a.w_numel + role.w_off[p] + u);   // 2 float4 per pair
+          const float4 c01 = __ldg(cp), c23 = __ldg(cp + 1);
+          const V2 a0 = make_float2(c01.x, c01.y), a1 = make_float2(c01.z, c01.w);
+          const V2 a2 = make_float2(c23.x, c23.y), a3 = make_float2(c23.z, c23.w);
+          w[p] = fma_(tt, fma_(tt, fma_(tt, a3, a2), a1), a0);
         } else {
-          w[p] = __ldg(a.w + (size_t)e * a.w_numel + role.w_off[p] + u);
+          w[p] = ldg2(a.w + (size_t)e * a.w_numel + role.w_off[p] + u);
         }
+        if (LPN != 32 && !valid) w[p] = splat2(0.0f);
       }
       Kind::fwd(x, Y, w, acc[c]);
     }
   }
 
-  float* __restrict__ orow = out + (size_t)n * a.dim_mid;
+  if (!m.node_ok) return;
+  float* __restrict__ orow = out + (size_t)m.n * a.dim_mid;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int u = u0 + 32 * c;
+  for (int c = 0; c < NV; ++c) {
+    const int u = m.uc0 + 2 * LPN * c;
 #pragma unroll
     for (int p = 0; p < Kind::NPATH; ++p) {
 #pragma unroll
       for (int k = 0; k < 2 * Kind::path_l3(p) + 1; ++k)
-        orow[role.out_off[p] + k * role.out_stride[p] + u] = acc[c][Kind::acc_off(p) + k];
+        *reinterpret_cast<float2*>(orow + role.out_off[p] + k * role.out_stride[p] + u) = acc[c][Kind::acc_off(p) + k];
     }
   }
 }
@@ -124,99 +156,96 @@ conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) 
 // backward (centre-major): given ga = dE/d out[n, :], per edge of row n
 //   TABLE : dEdr_acc[e] += sum_{p,u} (dE/dw_{p,u}) * w'_{p,u}(r_e)         (radial chain rule)
 //   !TABLE: dw[e, :]     = dE/dw                                          (plug-in boundary)
-//   dY_acc[e, 1..]      += sum_u dE/dY                                    (warp reduction)
-//   dx[src_e, :]        += dE/dx                                          (RED.ADD, NEED_DX)
-// dY_acc / dEdr_acc / dw rows are owned by exactly one warp of one launch: plain read-modify-write.
+//   dY_acc[e, 1..]      += sum_u dE/dY                                    (group reduction)
+//   dx[src_e, :]        += dE/dx                                          (RED.ADD.F32x2, NEED_DX)
+// dY_acc / dEdr_acc / dw rows are owned by exactly one group of one launch: plain read-modify-write.
 // ------------------------------------------------------------------------------------------
-template <class Kind, int NCH, bool TABLE, bool NEED_DX>
+template <class Kind, int NV, int LPN, bool TABLE, bool NEED_DX>
 __global__ void __launch_bounds__(32 * kConvWarpsPerBlock)
 conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__ gout,
                 float* __restrict__ dx, float* __restrict__ dY_acc, float* __restrict__ dEdr_acc,
                 float* __restrict__ dw) {
-  const int n = blockIdx.x * kConvWarpsPerBlock + (threadIdx.x >> 5);
-  if (n >= a.n_dst) return;
-  const int lane = threadIdx.x & 31;
-  const int u0 = blockIdx.y * (32 * NCH) + lane;
-  const int e0 = __ldg(a.rowptr + n), e1 = __ldg(a.rowptr + n + 1);
+  const LaneMap<NV, LPN> m(a);
+  if (m.nmax == 0) return;                    // uniform: no edges in any row of this warp
 
-  float ga[NCH][Kind::NACC];
+  V2 ga[NV][Kind::NACC];
   {
-    const float* __restrict__ grow = gout + (size_t)n * a.dim_mid;
+    const float* __restrict__ grow = gout + (size_t)(m.node_ok ? m.n : 0) * a.dim_mid;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int u = u0 + 32 * c;
+    for (int c = 0; c < NV; ++c) {
+      const int u = m.uc0 + 2 * LPN * c;
 #pragma unroll
       for (int p = 0; p < Kind::NPATH; ++p)
 #pragma unroll
         for (int k = 0; k < 2 * Kind::path_l3(p) + 1; ++k)
-          ga[c][Kind::acc_off(p) + k] = __ldg(grow + role.out_off[p] + k * role.out_stride[p] + u);
+          ga[c][Kind::acc_off(p) + k] = ldg2(grow + role.out_off[p] + k * role.out_stride[p] + u);
     }
   }
 
   constexpr int NR = (Kind::NY <= 9) ? 8 : 16;   // values reduced with the transposing butterfly
-  for (int e = e0; e < e1; ++e) {
+  for (int it = 0; it < m.nmax; ++it) {
+    const bool valid = (LPN == 32) || (it < m.len);
+    const int e = valid ? m.e0 + it : 0;
     const int4 rec = __ldg(a.rec + e);
     float Y[Kind::NY];
     load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y);
     const float* __restrict__ xrow = a.x + (size_t)rec.x * a.dim_x + role.x_off;
     const float tt = __int_as_float(rec.z);
-    float dY[Kind::NY];
+    V2 dY[Kind::NY];
 #pragma unroll
-    for (int j = 0; j < Kind::NY; ++j) dY[j] = 0.0f;
-    float dEdr = 0.0f;
+    for (int j = 0; j < Kind::NY; ++j) dY[j] = splat2(0.0f);
+    V2 dEdr2 = splat2(0.0f);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int u = u0 + 32 * c;
-      float x[Kind::D1], w[Kind::NPATH], wd[Kind::NPATH], dwv[Kind::NPATH], dxv[Kind::D1];
+    for (int c = 0; c < NV; ++c) {
+      const int u = m.uc0 + 2 * LPN * c;
+      V2 x[Kind::D1], w[Kind::NPATH], wd[Kind::NPATH], dwv[Kind::NPATH], dxv[Kind::D1];
 #pragma unroll
-      for (int i = 0; i < Kind::D1; ++i) x[i] = __ldg(xrow + i * role.mul + u);
+      for (int i = 0; i < Kind::D1; ++i) x[i] = ldg2(xrow + i * role.mul + u);
 #pragma unroll
       for (int p = 0; p < Kind::NPATH; ++p) {
         if (TABLE) {
-          const float4 cf = __ldg(a.table + (size_t)rec.y * a.w_numel + role.w_off[p] + u);
-          w[p] = fmaf(tt, fmaf(tt, fmaf(tt, cf.w, cf.z), cf.y), cf.x);
-          wd[p] = fmaf(tt, fmaf(tt, 3.0f * cf.w, 2.0f * cf.z), cf.y) * a.inv_h;
+          const float4* cp = a.table + ((size_t)rec.y * a.w_numel + role.w_off[p] + u);
+          const float4 c01 = __ldg(cp), c23 = __ldg(cp + 1);
+          const V2 a0 = make_float2(c01.x, c01.y), a1 = make_float2(c01.z, c01.w);
+          const V2 a2 = make_float2(c23.x, c23.y), a3 = make_float2(c23.z, c23.w);
+          w[p] = fma_(tt, fma_(tt, fma_(tt, a3, a2), a1), a0);
+          wd[p] = mul_(fma_(tt, fma_(3.0f * tt, a3, mul_(a2, 2.0f)), a1), a.inv_h);
         } else {
-          w[p] = __ldg(a.w + (size_t)e * a.w_numel + role.w_off[p] + u);
-          wd[p] = 0.0f;
+          w[p] = ldg2(a.w + (size_t)e * a.w_numel + role.w_off[p] + u);
         }
       }
       Kind::bwd(x, Y, w, ga[c], dwv, dxv, dY);
+      if (valid) {
 #pragma unroll
-      for (int p = 0; p < Kind::NPATH; ++p) {
-        if (TABLE) dEdr = fmaf(dwv[p], wd[p], dEdr);
-        else dw[(size_t)e * a.w_numel + role.w_off[p] + u] = dwv[p];
-      }
-      if (NEED_DX) {
-        float* __restrict__ dxrow = dx + (size_t)rec.x * a.dim_x + role.x_off;
+        for (int p = 0; p < Kind::NPATH; ++p) {
+          if (TABLE) dEdr2 = fma_(dwv[p], wd[p], dEdr2);
+          else *reinterpret_cast<float2*>(dw + (size_t)e * a.w_numel + role.w_off[p] + u) = dwv[p];
+        }
+        if (NEED_DX) {
+          float* __restrict__ dxrow = dx + (size_t)rec.x * a.dim_x + role.x_off;
 #pragma unroll
-        for (int i = 0; i < Kind::D1; ++i) atomicAdd(dxrow + i * role.mul + u, dxv[i]);
-      }
-    }
-    // cross-channel reduction of dE/dY (NY-1 values) and dE/dr (1 value)
-    if (Kind::NY > 1) {
-      float red[NR];
-#pragma unroll
-      for (int j = 0; j < NR; ++j) red[j] = (j + 1 < Kind::NY) ? dY[j + 1] : 0.0f;
-      if (TABLE && Kind::NY - 1 < NR) red[NR - 1] = dEdr;     // free slot: ride along
-      warp_reduce_multi<NR>(red, lane);
-      constexpr int SH = (NR == 8) ? 2 : 1;
-      const int idx = (lane >> SH) & (NR - 1);
-      if ((lane & ((1 << SH) - 1)) == 0) {
-        if (idx + 1 < Kind::NY) {
-          float* p = dY_acc + (size_t)e * a.ny_stride + idx;
-          *p += red[0];
-        } else if (TABLE && Kind::NY - 1 < NR && idx == NR - 1) {
-          dEdr_acc[e] += red[0];
+          for (int i = 0; i < Kind::D1; ++i)
+            atomicAdd(reinterpret_cast<float2*>(dxrow + i * role.mul + u), dxv[i]);
         }
       }
-      if (TABLE && !(Kind::NY - 1 < NR)) {
-        const float s = warp_sum(dEdr);
-        if (lane == 0) dEdr_acc[e] += s;
-      }
-    } else if (TABLE) {
-      const float s = warp_sum(dEdr);
-      if (lane == 0) dEdr_acc[e] += s;
+    }
+    // cross-channel reduction of dE/dY (NY-1 values) and dE/dr (1 value) over the group
+    const float dEdr = dEdr2.x + dEdr2.y;
+    constexpr bool RIDE = TABLE && (Kind::NY - 1 < NR);     // a free slot carries dE/dr
+    float red[NR];
+#pragma unroll
+    for (int j = 0; j < NR; ++j) red[j] = (j + 1 < Kind::NY) ? dY[j + 1].x + dY[j + 1].y : 0.0f;
+    if (RIDE) red[NR - 1] = dEdr;
+    group_reduce_multi<NR, LPN>(red, m.sl);
+    constexpr int PER = LPN / NR;
+    const int idx = (m.sl / PER) % NR;
+    if (valid && (m.sl % PER) == 0) {
+      if (idx + 1 < Kind::NY) dY_acc[(size_t)e * a.ny_stride + idx] += red[0];
+      else if (RIDE && idx == NR - 1) dEdr_acc[e] += red[0];
+    }
+    if (TABLE && !RIDE) {
+      const float s = group_sum<LPN>(dEdr);
+      if (valid && m.sl == 0) dEdr_acc[e] += s;
     }
   }
 }

@@ -84,7 +84,7 @@ def gen_kind(l1: int, lf: int, lo: int) -> str:
                 for i, j, k in zip(*np.nonzero(c)):
                     need.add((int(i), int(j)))
             for (i, j) in sorted(need):
-                lines.append(f'    const float t{l2}_{i}_{j} = x[{i}] * {_y(l2, j)};')
+                lines.append(f'    const V t{l2}_{i}_{j} = mul_(x[{i}], {_y(l2, j)});')
 
     def s_expr(l2: int, l3: int, k: int) -> str:
         c = tp_path_coefficients(l1, l2, l3)
@@ -95,41 +95,41 @@ def gen_kind(l1: int, lf: int, lo: int) -> str:
                 if v != 0.0:
                     t = f'x[{i}]' if l2 == 0 else f't{l2}_{i}_{j}'
                     terms.append((v, t))
-        if not terms:
-            return '0.0f'
-        e = f'{_f(terms[0][0])} * {terms[0][1]}'
+        assert terms
+        e = terms[0][1] if abs(terms[0][0] - 1.0) < 1e-12 else f'mul_({terms[0][1]}, {_f(terms[0][0])})'
         for v, t in terms[1:]:
-            e = f'fmaf({_f(v)}, {t}, {e})'
+            e = f'fma_({_f(v)}, {t}, {e})'
         return e
 
     # ---- forward
     out.append('  // acc[ACC_OFF[p] + k] += w[p] * sum_ij C\'[i,j,k] x[i] Y[j]')
-    out.append('  S7B_HD static void fwd(const float* __restrict__ x, const float* __restrict__ Y,')
-    out.append('                                const float* __restrict__ w, float* __restrict__ acc) {')
+    out.append('  template <class V>')
+    out.append('  S7B_HD static void fwd(const V* __restrict__ x, const float* __restrict__ Y,')
+    out.append('                         const V* __restrict__ w, V* __restrict__ acc) {')
     body: List[str] = []
     products(body)
     for p, (l2, l3) in enumerate(paths):
         for k in range(2 * l3 + 1):
-            body.append(f'    acc[{acc_off[p] + k}] = fmaf(w[{p}], {s_expr(l2, l3, k)}, acc[{acc_off[p] + k}]);')
+            body.append(f'    acc[{acc_off[p] + k}] = fma_(w[{p}], {s_expr(l2, l3, k)}, acc[{acc_off[p] + k}]);')
     out += body
     out.append('  }')
 
     # ---- backward
     out.append('  // dw[p] = ...; dx[i] = ...; dY[j] += ... (see header comment of gen_kernels.py)')
-    out.append('  S7B_HD static void bwd(const float* __restrict__ x, const float* __restrict__ Y,')
-    out.append('                                const float* __restrict__ w, const float* __restrict__ ga,')
-    out.append('                                float* __restrict__ dw, float* __restrict__ dx, float* __restrict__ dY) {')
+    out.append('  template <class V>')
+    out.append('  S7B_HD static void bwd(const V* __restrict__ x, const float* __restrict__ Y,')
+    out.append('                         const V* __restrict__ w, const V* __restrict__ ga,')
+    out.append('                         V* __restrict__ dw, V* __restrict__ dx, V* __restrict__ dY) {')
     body = []
     products(body)
     for p, (l2, l3) in enumerate(paths):
-        terms = [f'ga[{acc_off[p] + k}] * ({s_expr(l2, l3, k)})' for k in range(2 * l3 + 1)]
-        e = terms[0]
-        for t in terms[1:]:
-            e = f'{e} + {t}'
+        e = f'mul_(ga[{acc_off[p]}], {s_expr(l2, l3, 0)})'
+        for k in range(1, 2 * l3 + 1):
+            e = f'fma_(ga[{acc_off[p] + k}], {s_expr(l2, l3, k)}, {e})'
         body.append(f'    dw[{p}] = {e};')
     for p, (l2, l3) in enumerate(paths):
         for k in range(2 * l3 + 1):
-            body.append(f'    const float g{p}_{k} = w[{p}] * ga[{acc_off[p] + k}];')
+            body.append(f'    const V g{p}_{k} = mul_(w[{p}], ga[{acc_off[p] + k}]);')
     for i in range(d1):
         dx_terms = []
         for l2 in l2_used:
@@ -144,14 +144,19 @@ def gen_kind(l1: int, lf: int, lo: int) -> str:
                             terms.append((c[i, j, k], f'g{p}_{k}'))
                 if not terms:
                     continue
-                e = f'{_f(terms[0][0])} * {terms[0][1]}'
+                e = terms[0][1] if abs(terms[0][0] - 1.0) < 1e-12 else f'mul_({terms[0][1]}, {_f(terms[0][0])})'
                 for v, t in terms[1:]:
-                    e = f'fmaf({_f(v)}, {t}, {e})'
-                body.append(f'    const float r{l2}_{i}_{j} = {e};')
-                dx_terms.append(f'r{l2}_{i}_{j}' if l2 == 0 else f'r{l2}_{i}_{j} * {_y(l2, j)}')
+                    e = f'fma_({_f(v)}, {t}, {e})'
+                body.append(f'    const V r{l2}_{i}_{j} = {e};')
+                dx_terms.append((l2, j, f'r{l2}_{i}_{j}'))
                 if l2 > 0:
-                    body.append(f'    dY[{l2 * l2 + j}] = fmaf(x[{i}], r{l2}_{i}_{j}, dY[{l2 * l2 + j}]);')
-        body.append(f'    dx[{i}] = {" + ".join(dx_terms) if dx_terms else "0.0f"};')
+                    body.append(f'    dY[{l2 * l2 + j}] = fma_(x[{i}], r{l2}_{i}_{j}, dY[{l2 * l2 + j}]);')
+        assert dx_terms
+        l2_, j_, r_ = dx_terms[0]
+        e = r_ if l2_ == 0 else f'mul_({r_}, {_y(l2_, j_)})'
+        for (l2_, j_, r_) in dx_terms[1:]:
+            e = f'add_({r_}, {e})' if l2_ == 0 else f'fma_({_y(l2_, j_)}, {r_}, {e})'
+        body.append(f'    dx[{i}] = {e};')
     out += body
     out.append('  }')
     out.append('};')
@@ -221,14 +226,7 @@ def _cc(expr, sub=None) -> str:
 
 HEADER = '''// GENERATED by sevenn_b200/csrc/gen_kernels.py -- do not edit by hand.
 #pragma once
-#ifndef S7B_HD
-#if defined(__CUDACC__)
-#define S7B_HD __host__ __device__ __forceinline__
-#else
-#define S7B_HD inline
-#include <cmath>
-#endif
-#endif
+#include "../vec_ops.cuh"
 '''
 
 

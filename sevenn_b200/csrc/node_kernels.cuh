@@ -37,10 +37,11 @@ struct LinArgs {
   LinBlock blk[kMaxL];
 };
 
-constexpr int kGemmBM = 64, kGemmBN = 64, kGemmBK = 16, kGemmThreads = 256;
+constexpr int kGemmBM = 128, kGemmBN = 64, kGemmBK = 16, kGemmThreads = 256;
 constexpr int kGemmPadM = kGemmBM + 4;
 
-// grid = (ceil(max rows / BM), ceil(max N / BN), nblocks)
+// FP32 SIMT GEMM tile: 128 x 64 per CTA, 8 x 4 per thread, inner product issued as packed FFMA2
+// (scalar-broadcast A element x a pair of B columns).  grid = (ceil(max rows / BM), ceil(max N / BN), nblocks)
 __global__ void __launch_bounds__(kGemmThreads) blocklin_gemm_kernel(const LinArgs a) {
   const LinBlock b = a.blk[blockIdx.z];
   const int rows = a.n_nodes * b.d;
@@ -52,34 +53,39 @@ __global__ void __launch_bounds__(kGemmThreads) blocklin_gemm_kernel(const LinAr
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  // A loader: thread -> (row, k-quad)
+  // A loader: thread -> rows (tid/4, tid/4 + 64), k-quad tid%4
   const int a_row = tid >> 2, a_kq = tid & 3;
-  const int gr = row0 + a_row;
-  const float* a_ptr = nullptr;
-  if (gr < rows) {
-    const int n = gr / b.d, i = gr - n * b.d;
-    a_ptr = a.A + (size_t)n * a.lda + b.a_off + i * b.a_cs;
+  const float* a_ptr[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int gr = row0 + a_row + 64 * h;
+    a_ptr[h] = nullptr;
+    if (gr < rows) {
+      const int n = gr / b.d, i = gr - n * b.d;
+      a_ptr[h] = a.A + (size_t)n * a.lda + b.a_off + i * b.a_cs;
+    }
   }
   // B loader: thread -> (k, col-quad)
   const int b_k = tid >> 4, b_cq = tid & 15;
   const int gc = col0 + b_cq * 4;
 
-  float acc[4][4];
+  V2 acc[8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = splat2(0.0f);
 
-  float4 ra, rb;
+  float4 ra[2], rb;
   auto load_tiles = [&](int k0) {
-    ra = make_float4(0.f, 0.f, 0.f, 0.f);
     const int ka = k0 + a_kq * 4;
-    if (a_ptr != nullptr) {
-      if (ka + 3 < b.K) ra = __ldg(reinterpret_cast<const float4*>(a_ptr + ka));
-      else {
-        if (ka + 0 < b.K) ra.x = __ldg(a_ptr + ka + 0);
-        if (ka + 1 < b.K) ra.y = __ldg(a_ptr + ka + 1);
-        if (ka + 2 < b.K) ra.z = __ldg(a_ptr + ka + 2);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_ptr[h] != nullptr) {
+        if (ka + 3 < b.K) ra[h] = __ldg(reinterpret_cast<const float4*>(a_ptr[h] + ka));
+        else {
+          if (ka + 0 < b.K) ra[h].x = __ldg(a_ptr[h] + ka + 0);
+          if (ka + 1 < b.K) ra[h].y = __ldg(a_ptr[h] + ka + 1);
+          if (ka + 2 < b.K) ra[h].z = __ldg(a_ptr[h] + ka + 2);
+        }
       }
     }
     rb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -95,10 +101,13 @@ __global__ void __launch_bounds__(kGemmThreads) blocklin_gemm_kernel(const LinAr
     }
   };
   auto store_tiles = [&]() {
-    As[a_kq * 4 + 0][a_row] = ra.x;
-    As[a_kq * 4 + 1][a_row] = ra.y;
-    As[a_kq * 4 + 2][a_row] = ra.z;
-    As[a_kq * 4 + 3][a_row] = ra.w;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      As[a_kq * 4 + 0][a_row + 64 * h] = ra[h].x;
+      As[a_kq * 4 + 1][a_row + 64 * h] = ra[h].y;
+      As[a_kq * 4 + 2][a_row + 64 * h] = ra[h].z;
+      As[a_kq * 4 + 3][a_row + 64 * h] = ra[h].w;
+    }
     *reinterpret_cast<float4*>(&Bs[b_k][b_cq * 4]) = rb;
   };
 
@@ -109,29 +118,32 @@ __global__ void __launch_bounds__(kGemmThreads) blocklin_gemm_kernel(const LinAr
     if (k0 + kGemmBK < b.K) load_tiles(k0 + kGemmBK);
 #pragma unroll
     for (int k = 0; k < kGemmBK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
       const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float aa[4] = {av.x, av.y, av.z, av.w};
-      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+      const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const V2 b0 = make_float2(bv.x, bv.y), b1 = make_float2(bv.z, bv.w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fma_(aa[i], b0, acc[i][0]);
+        acc[i][1] = fma_(aa[i], b1, acc[i][1]);
+      }
     }
     __syncthreads();
   }
 
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = row0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int r = row0 + ty * 8 + i;
     if (r >= rows) continue;
     const int n = r / b.d, ii = r - n * b.d;
     const size_t coff = (size_t)n * a.ldc + b.c_off + ii * b.c_cs;
+    const float vals[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = col0 + tx * 4 + j;
       if (c >= b.N) continue;
-      float v = acc[i][j];
+      float v = vals[j];
       if (a.accumulate) v += a.C[coff + c];
       if (a.epilogue == kEpiSiluStoreZ) {
         a.aux_out[coff + c] = v;

@@ -157,6 +157,14 @@ def radial_table(spec: ModelSpec, arrays: Dict[str, np.ndarray], t: int, knots: 
     return np.ascontiguousarray(tab, dtype=np.float32)
 
 
+def pack_table_pairs(tab: np.ndarray) -> np.ndarray:
+    """[knots, W, 4] -> device layout [knots, W/2, 4 (coefficient), 2 (even/odd channel)]: the two
+    float4 a lane loads for its channel pair are {a0e,a0o,a1e,a1o} and {a2e,a2o,a3e,a3o}, i.e. every
+    coefficient arrives as an aligned register pair for the packed FFMA2 Horner evaluation."""
+    K, W, _ = tab.shape
+    return np.ascontiguousarray(tab.reshape(K, W // 2, 2, 4).transpose(0, 1, 3, 2))
+
+
 def default_table_knots(spec: ModelSpec) -> int:
     """A grid on which the XPLOR switching radius (a C1-only point) is a knot."""
     return 2000 if spec.cutoff_fn == 'XPLOR' else 2048
@@ -202,7 +210,7 @@ def prepare_params(spec: ModelSpec, arrays: Dict[str, np.ndarray], radial: str, 
         out[('si2', t)] = np.concatenate([b.ravel() for b in si2])
         out[('si2T', t)] = np.concatenate([b.T.ravel() for b in si2])
         if radial == 'table':
-            out[('table', t)] = radial_table(spec, arrays, t, knots)
+            out[('table', t)] = pack_table_pairs(radial_table(spec, arrays, t, knots))
         else:
             for j in range(len(spec.radial_hidden) + 1):
                 W = f64(arrays[f'{t}.mlp{j}'])

@@ -35,6 +35,22 @@ int tp_bwd(int l1, int lf, int lo, const float* x, const float* Y, const float* 
   return 1;
 }
 
+// packed-pair instantiation (two channels per "lane"): arrays of V2 = {x, y}
+int tp_fwd2(int l1, int lf, int lo, const float* x, const float* Y, const float* w, float* acc) {
+#define X(a,b,c) if (l1==a && lf==b && lo==c) { TPKind<a,b,c>::fwd(reinterpret_cast<const V2*>(x), Y, reinterpret_cast<const V2*>(w), reinterpret_cast<V2*>(acc)); return 0; }
+  FOR_KINDS(X)
+#undef X
+  return 1;
+}
+
+int tp_bwd2(int l1, int lf, int lo, const float* x, const float* Y, const float* w, const float* ga,
+            float* dw, float* dx, float* dY) {
+#define X(a,b,c) if (l1==a && lf==b && lo==c) { TPKind<a,b,c>::bwd(reinterpret_cast<const V2*>(x), Y, reinterpret_cast<const V2*>(w), reinterpret_cast<const V2*>(ga), reinterpret_cast<V2*>(dw), reinterpret_cast<V2*>(dx), reinterpret_cast<V2*>(dY)); return 0; }
+  FOR_KINDS(X)
+#undef X
+  return 1;
+}
+
 int sh_eval(int lmax, float x, float y, float z, float* Y) {
   if (lmax == 1) { SH<1>::eval(x, y, z, Y); return 0; }
   if (lmax == 2) { SH<2>::eval(x, y, z, Y); return 0; }

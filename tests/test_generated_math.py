@@ -76,6 +76,33 @@ def test_tp_kind_forward_backward(lib, l1, lf, lo):
     assert np.allclose(dY - dY0, dY_ref, atol=3e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize('l1,lf,lo', KINDS)
+def test_tp_kind_packed_pair_instantiation_matches_scalar(lib, l1, lf, lo):
+    """The V2 (two channels per lane, FFMA2 on the GPU) instantiation of the generated code equals
+    two independent scalar evaluations."""
+    npath, nacc = ctypes.c_int(), ctypes.c_int()
+    t = [np.zeros(16, np.int32) for _ in range(3)]
+    ip = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+    lib.tp_info(l1, lf, lo, ctypes.byref(npath), ctypes.byref(nacc), ip(t[0]), ip(t[1]), ip(t[2]))
+    npath, nacc = npath.value, nacc.value
+    rng = np.random.RandomState(7 + l1)
+    d1, ny = 2 * l1 + 1, (lf + 1) ** 2
+    Y = spherical_harmonics(lf, rng.normal(size=3)).astype(np.float32)
+    x2, w2, ga2 = (rng.normal(size=(n, 2)).astype(np.float32) for n in (d1, npath, nacc))
+    acc2 = np.zeros((nacc, 2), np.float32)
+    dw2, dx2, dY2 = np.zeros((npath, 2), np.float32), np.zeros((d1, 2), np.float32), np.zeros((ny, 2), np.float32)
+    assert lib.tp_fwd2(l1, lf, lo, fp(x2), fp(Y), fp(w2), fp(acc2)) == 0
+    assert lib.tp_bwd2(l1, lf, lo, fp(x2), fp(Y), fp(w2), fp(ga2), fp(dw2), fp(dx2), fp(dY2)) == 0
+    for h in range(2):
+        x, w, ga = (np.ascontiguousarray(a[:, h]) for a in (x2, w2, ga2))
+        acc = np.zeros(nacc, np.float32)
+        dw, dx, dY = np.zeros(npath, np.float32), np.zeros(d1, np.float32), np.zeros(ny, np.float32)
+        lib.tp_fwd(l1, lf, lo, fp(x), fp(Y), fp(w), fp(acc))
+        lib.tp_bwd(l1, lf, lo, fp(x), fp(Y), fp(w), fp(ga), fp(dw), fp(dx), fp(dY))
+        assert np.allclose(acc2[:, h], acc, atol=1e-6) and np.allclose(dw2[:, h], dw, atol=1e-6)
+        assert np.allclose(dx2[:, h], dx, atol=1e-6) and np.allclose(dY2[:, h], dY, atol=1e-6)
+
+
 @pytest.mark.parametrize('lmax', [1, 2, 3])
 def test_sh_eval_and_vjp(lib, lmax):
     rng = np.random.RandomState(lmax)
