@@ -176,7 +176,8 @@ def run_engine(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{args.model}.npz'))
     tm = {int(k): int(v) for k, v in meta['type_map'].items()}
@@ -241,16 +242,17 @@ def run_engine(args):
     value = n_atoms * args.steps / (total_ms * 1e-3)
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) ---------------------------
+    # (every rank runs the same steps -- the exchanges are collective; only rank 0 records events)
     roofline, breakdown = None, None
+    eng.set_profiling(rank == 0)
+    for _ in range(min(args.steps, 10)):
+        flush.fill_(1)
+        step()
+    torch.cuda.synchronize()
     if rank == 0:
-        eng.set_profiling(True)
-        for _ in range(min(args.steps, 10)):
-            flush.fill_(1)
-            step()
-        torch.cuda.synchronize()
         prof = eng.profile()
-        eng.set_profiling(False)
         roofline, breakdown = roofline_from_profile(eng, prof, n_edges if world == 1 else n_edges_local, eng.n_local)
+    eng.set_profiling(False)
 
     # ---- end to end through the host-buffer entry (N = 1) or the runner's host path (N > 1) -------
     if world == 1:
