@@ -75,6 +75,15 @@ enum {
 S7B_API const char* s7b_last_error(void);
 S7B_API int s7b_version(void);
 
+/* Runtime options: "tc_gemm" (default 1) runs the node linears on tcgen05 tensor cores (3xTF32,
+ * fp32-level accuracy); 0 selects the FP32 SIMT GEMM kernel. */
+S7B_API int s7b_set_option(const char* name, int value);
+
+/* C[rows, N] = A[rows, K] * W[K, N] (row-major, device pointers) through the same GEMM kernels the
+ * engine uses for its linears; use_tc selects the tcgen05 path (needs K % 32 == 0, N % 16 == 0). */
+S7B_API int s7b_dense_linear(const float* A, const float* W, float* C, int64_t rows, int32_t K, int32_t N,
+                             int32_t use_tc, void* stream);
+
 /* ---- engine ---------------------------------------------------------------------------- */
 S7B_API int s7b_engine_create(const S7bModelDesc* desc, S7bEngine** out);
 S7B_API void s7b_engine_destroy(S7bEngine* eng);

@@ -19,6 +19,7 @@
 #include "conv_kernels.cuh"
 #include "edge_kernels.cuh"
 #include "node_kernels.cuh"
+#include "tc_gemm.cuh"
 
 namespace s7b {
 
@@ -275,6 +276,47 @@ static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* 
   return 0;
 }
 
+static int g_opt_tc_gemm = 1;   // node linears on tcgen05 (3xTF32) when shapes allow
+
+// hi = w truncated to TF32 (13 low mantissa bits cleared), lo = w - hi
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+// out[n, k] = in[k, n]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int K, int N) {
+  const size_t total = (size_t)K * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K), k = (int)(i - (size_t)n * K);
+    out[i] = in[(size_t)k * N + n];
+  }
+}
+
+static int launch_tc_gemm(const TcLinArgs& a, cudaStream_t st) {
+  int max_rows = 0, max_n = 0;
+  for (int b = 0; b < a.nblocks; ++b) {
+    max_rows = std::max(max_rows, a.n_nodes * a.blk[b].d);
+    max_n = std::max(max_n, a.blk[b].N);
+  }
+  if (max_rows == 0 || max_n == 0) return 0;
+  const int n_chunk = std::min(max_n, kTcMaxN);
+  const size_t smem = 2 * (2 * 16384 + 2 * (size_t)n_chunk * 128);
+  static size_t configured = 0;
+  if (smem > configured) {
+    S7B_CUDA_CHECK(cudaFuncSetAttribute(blocklin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((max_rows + kTcBM - 1) / kTcBM, (max_n + n_chunk - 1) / n_chunk, a.nblocks);
+  blocklin_tc_kernel<<<grid, kTcThreads, smem, st>>>(a, n_chunk);
+  S7B_LAUNCH_CHECK();
+  return 0;
+}
+
 static int launch_gemm(const LinArgs& a, cudaStream_t st) {
   int max_rows = 0, max_n = 0;
   for (int b = 0; b < a.nblocks; ++b) {
@@ -292,7 +334,39 @@ static int launch_gemm(const LinArgs& a, cudaStream_t st) {
 // stored one after another in `W`.  A blocks: (a_off[l], K = a_K[l]); C blocks: (c_off[l], N = c_N[l]).
 static int irreps_linear(const float* A, int lda, const int* a_off, const int* a_K, float* C, int ldc,
                          const int* c_off, const int* c_N, int n_l, const float* W, int n_nodes,
-                         bool accumulate, cudaStream_t st) {
+                         bool accumulate, cudaStream_t st, const float* Wt_hi = nullptr,
+                         const float* Wt_lo = nullptr) {
+  if (g_opt_tc_gemm && Wt_hi != nullptr && Wt_lo != nullptr) {
+    bool ok = true;
+    for (int l = 0; l < n_l; ++l)
+      if (a_K[l] != 0 && c_N[l] != 0 && (a_K[l] % kTcKC != 0 || c_N[l] % 16 != 0)) ok = false;
+    if (ok) {
+      TcLinArgs t;
+      memset(&t, 0, sizeof(t));
+      t.A = A;
+      t.C = C;
+      t.lda = lda;
+      t.ldc = ldc;
+      t.n_nodes = n_nodes;
+      t.accumulate = accumulate ? 1 : 0;
+      size_t woff = 0;
+      for (int l = 0; l < n_l; ++l) {
+        if (a_K[l] == 0 || c_N[l] == 0) continue;
+        TcLinBlock& b = t.blk[t.nblocks++];
+        b.Wt_hi = Wt_hi + woff;     // W^T blocks are stored in the same per-l order, [N, K] each
+        b.Wt_lo = Wt_lo + woff;
+        b.d = 2 * l + 1;
+        b.K = a_K[l];
+        b.N = c_N[l];
+        b.a_off = a_off[l];
+        b.a_cs = a_K[l];
+        b.c_off = c_off[l];
+        b.c_cs = c_N[l];
+        woff += (size_t)a_K[l] * c_N[l];
+      }
+      return launch_tc_gemm(t, st);
+    }
+  }
   LinArgs a;
   memset(&a, 0, sizeof(a));
   a.A = A;
@@ -362,6 +436,41 @@ int64_t s7b_launch_count(int reset) {
   const int64_t v = g_launches + g_conv_launches;
   if (reset) { g_launches = 0; g_conv_launches = 0; }
   return v;
+}
+
+int s7b_set_option(const char* name, int value) {
+  if (!name) return fail("null option name");
+  if (std::string(name) == "tc_gemm") { g_opt_tc_gemm = value; return 0; }
+  return fail(std::string("unknown option: ") + name);
+}
+
+int s7b_dense_linear(const float* A, const float* W, float* C, int64_t rows, int32_t K, int32_t N,
+                     int32_t use_tc, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (rows <= 0 || K <= 0 || N <= 0 || rows > (1 << 24)) return fail("bad sizes");
+  if (!use_tc) return dense_gemm(A, K, C, N, W, rows, kEpiNone, nullptr, nullptr, false, st);
+  if (K % kTcKC != 0 || N % 16 != 0) return fail("tensor-core linear needs K % 32 == 0 and N % 16 == 0");
+  float *wt = nullptr, *hi = nullptr, *lo = nullptr;
+  const size_t n = (size_t)K * N;
+  S7B_CUDA_CHECK(cudaMalloc((void**)&wt, 3 * n * sizeof(float)));
+  hi = wt + n;
+  lo = hi + n;
+  // W^T on the host side of the stream: small, done with a strided 2D copy
+  transpose_kernel<<<256, 256, 0, st>>>(W, wt, K, N);
+  split_tf32_kernel<<<256, 256, 0, st>>>(wt, hi, lo, n);
+  TcLinArgs t;
+  memset(&t, 0, sizeof(t));
+  t.A = A;
+  t.C = C;
+  t.lda = K;
+  t.ldc = N;
+  t.n_nodes = (int)rows;
+  t.nblocks = 1;
+  t.blk[0] = TcLinBlock{hi, lo, 1, K, N, 0, K, 0, N};
+  int rc = launch_tc_gemm(t, st);
+  cudaStreamSynchronize(st);
+  cudaFree(wt);
+  return rc;
 }
 
 int s7b_engine_create(const S7bModelDesc* d, S7bEngine** out) {
@@ -439,6 +548,13 @@ int s7b_engine_set_param(S7bEngine* e, const char* name, int layer, const float*
   }
   if (dst->ensure(numel * sizeof(float))) return fail("cudaMalloc failed for parameter " + nm);
   S7B_CUDA_CHECK(cudaMemcpy(dst->p, host, numel * sizeof(float), cudaMemcpyHostToDevice));
+  if (layer >= 0 && (nm == "si1" || nm == "si1T" || nm == "sc" || nm == "scT" || nm == "si2" || nm == "si2T")) {
+    DevBuf& hi = e->layers[layer].params[nm + ".hi"];
+    DevBuf& lo = e->layers[layer].params[nm + ".lo"];
+    if (hi.ensure(numel * sizeof(float)) || lo.ensure(numel * sizeof(float))) return fail("cudaMalloc failed for parameter " + nm);
+    split_tf32_kernel<<<256, 256>>>(dst->as<float>(), hi.as<float>(), lo.as<float>(), numel);
+    S7B_CUDA_CHECK(cudaDeviceSynchronize());
+  }
   return 0;
 }
 
@@ -617,7 +733,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       if (require(si2, "si2")) return 1;
       {
         ProfScope ps(e->prof, st, "si2_gemm", t);
-        if (irreps_linear(e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st)) return 1;
+        if (irreps_linear(e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st, lparam(e, t, "si2T.hi"), lparam(e, t, "si2T.lo"))) return 1;
       }
       // gate
       {
@@ -631,11 +747,11 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         if (require(si1, "si1") || require(sc, "sc")) return 1;
         ProfScope ps(e->prof, st, "si1_sc_gemm", t + 1);
         // self_interaction_1 of the next layer -> local rows of x[t+1]
-        if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st)) return 1;
+        if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st, lparam(e, t + 1, "si1T.hi"), lparam(e, t + 1, "si1T.lo"))) return 1;
         // self_connection_intro of the next layer -> initial value of g[t+1]
         S7B_CUDA_CHECK(cudaMemsetAsync(e->g[t + 1].p, 0, (size_t)Nl * N.dim_g * sizeof(float), st));
         const int n_sc = std::min(N.n_lx, N.n_lg);
-        if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->g[t + 1].as<float>(), N.dim_g, N.g_off, N.g_muls, n_sc, sc, Nl, false, st)) return 1;
+        if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->g[t + 1].as<float>(), N.dim_g, N.g_off, N.g_muls, n_sc, sc, Nl, false, st, lparam(e, t + 1, "scT.hi"), lparam(e, t + 1, "scT.lo"))) return 1;
       }
       return 0;
     }
@@ -667,7 +783,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       // d(mid) = dg * si2^T
       {
         ProfScope ps(e->prof, st, "si2T_gemm", t);
-        if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st)) return 1;
+        if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st, lparam(e, t, "si2.hi"), lparam(e, t, "si2.lo"))) return 1;
       }
       if (E > 0) {
         ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
@@ -698,9 +814,9 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       if (require(si1T, "si1T") || require(scT, "scT")) return 1;
       // dE/dh(t) = dx(t) * si1^T + dg(t) * sc^T     (h(t) = gate output of layer t-1)
       ProfScope ps(e->prof, st, "si1T_scT_gemm", t);
-      if (irreps_linear(e->dx.as<float>(), L.dim_x, L.x_off, L.x_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, L.n_lx, si1T, Nl, false, st)) return 1;
+      if (irreps_linear(e->dx.as<float>(), L.dim_x, L.x_off, L.x_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, L.n_lx, si1T, Nl, false, st, lparam(e, t, "si1.hi"), lparam(e, t, "si1.lo"))) return 1;
       const int n_sc = std::min(L.n_lx, L.n_lg);
-      if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, n_sc, scT, Nl, true, st)) return 1;
+      if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, n_sc, scT, Nl, true, st, lparam(e, t, "sc.hi"), lparam(e, t, "sc.lo"))) return 1;
       return 0;
     }
     case S7B_STAGE_BWD_END: {

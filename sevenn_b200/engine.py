@@ -46,7 +46,7 @@ class S7bModelDesc(ctypes.Structure):
 
 
 EXPORTS = [
-    's7b_last_error', 's7b_version', 's7b_engine_create', 's7b_engine_destroy',
+    's7b_last_error', 's7b_version', 's7b_set_option', 's7b_dense_linear', 's7b_engine_create', 's7b_engine_destroy',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
     's7b_engine_buffer', 's7b_engine_compute_host', 's7b_launch_count', 's7b_engine_set_profiling',
     's7b_engine_profile_count', 's7b_engine_profile_entry', 's7b_conv_plan_create',
@@ -66,6 +66,8 @@ def load_library() -> ctypes.CDLL:
     lib = ctypes.CDLL(_LIB_PATH)
     vp, i32, i64, sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
     lib.s7b_last_error.restype = ctypes.c_char_p
+    lib.s7b_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.s7b_dense_linear.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.s7b_engine_create.argtypes = [ctypes.POINTER(S7bModelDesc), ctypes.POINTER(vp)]
     lib.s7b_engine_destroy.argtypes = [vp]
     lib.s7b_engine_destroy.restype = None
@@ -90,6 +92,10 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_conv_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, vp, vp, vp]
     _lib = lib
     return lib
+
+
+def set_option(name: str, value: int) -> None:
+    check(load_library().s7b_set_option(name.encode(), int(value)))
 
 
 def check(rc: int) -> None:
