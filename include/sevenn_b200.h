@@ -75,8 +75,9 @@ enum {
 S7B_API const char* s7b_last_error(void);
 S7B_API int s7b_version(void);
 
-/* Runtime options: "tc_gemm" (default 1) runs the node linears on tcgen05 tensor cores (3xTF32,
- * fp32-level accuracy); 0 selects the FP32 SIMT GEMM kernel. */
+/* Runtime options: "tc_gemm" = 1 runs the node linears on tcgen05 tensor cores (3xTF32 with TMEM
+ * accumulators; ~5e-7 relative error with a small systematic component from the tensor core's
+ * truncating accumulation); 0 (default) selects the FP32 SIMT GEMM kernel (IEEE fp32 FMA chain). */
 S7B_API int s7b_set_option(const char* name, int value);
 
 /* C[rows, N] = A[rows, K] * W[K, N] (row-major, device pointers) through the same GEMM kernels the

@@ -276,15 +276,15 @@ static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* 
   return 0;
 }
 
-static int g_opt_tc_gemm = 1;   // node linears on tcgen05 (3xTF32) when shapes allow
+static int g_opt_tc_gemm = 0;   // 1: node linears on tcgen05 (3xTF32); default FP32 SIMT
 
-// hi = w truncated to TF32 (13 low mantissa bits cleared), lo = w - hi
+// hi = rna_tf32(w), lo = rna_tf32(w - hi)   (see tc_gemm.cuh)
 __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = w[i];
-    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const float h = rna_tf32(v);
     hi[i] = h;
-    lo[i] = v - h;
+    lo[i] = rna_tf32(v - h);
   }
 }
 

@@ -3,15 +3,16 @@
 // Same operand addressing as blocklin_gemm_kernel (node_kernels.cuh); replaces e3nn o3.Linear
 // (sevenn/nn/linear.py:94-100) for self_interaction_1/2 and the self connection.
 //
-// Precision: every fp32 operand is split a = a_hi + a_lo with a_hi = a truncated to TF32 (top 19
-// bits) and a_lo = a - a_hi (exact); the tensor core accumulates a_hi*b_hi + a_lo*b_hi + a_hi*b_lo
-// in fp32 in TMEM (error ~2^-21 relative, i.e. fp32-level).  Weights are pre-split on the host.
+// Precision: every fp32 operand is split a = a_hi + a_lo with a_hi = rna_tf32(a) and
+// a_lo = rna_tf32(a - a_hi) (round-to-nearest, so the hardware's truncation to TF32 loses nothing and
+// the residual 2^-23-level errors are unbiased); the tensor core accumulates all four products
+// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo + a_lo*b_lo in fp32 in TMEM.  Weights are pre-split once.
 //
 // Structure (one CTA = 128 threads = one 128-row tile x one N chunk of <= 256 columns):
 //   * all threads stage a [128 x 32] A chunk (split hi/lo on the fly) and the matching
 //     [N x 32] W^T chunk into shared memory in the canonical K-major, no-swizzle UMMA layout
 //     (8-row x 16-byte core matrices; LBO = 128 B along K, SBO = 1024 B between row groups);
-//   * one elected thread issues 12 tcgen05.mma.kind::tf32 (M=128, N, K=8) per chunk and commits to an
+//   * one elected thread issues 16 tcgen05.mma.kind::tf32 (M=128, N, K=8) per chunk and commits to an
 //     mbarrier; two stages, so the loads of chunk c+1 overlap the MMAs of chunk c;
 //   * the accumulator [128 x N] fp32 lives in TMEM; after the last commit each warp reads its 32
 //     lanes with tcgen05.ld.32x32b.x32 and writes the rows out (optionally C += ...).
@@ -80,6 +81,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// round-to-nearest conversion to a TF32-representable fp32 value (the tensor core itself would truncate)
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
 }
 
 // canonical K-major no-swizzle offset (bytes) of the 16-byte chunk (row r, k-quad q) in a [rows x 32] tile
@@ -155,10 +163,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) blocklin_tc_kernel(const TcLinA
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a_row != nullptr) v = __ldg(reinterpret_cast<const float4*>(a_row + kc * kTcKC + 4 * q));
       float4 h, l;
-      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+      h.x = rna_tf32(v.x); l.x = rna_tf32(v.x - h.x);
+      h.y = rna_tf32(v.y); l.y = rna_tf32(v.y - h.y);
+      h.z = rna_tf32(v.z); l.z = rna_tf32(v.z - h.z);
+      h.w = rna_tf32(v.w); l.w = rna_tf32(v.w - h.w);
       const uint32_t off = canon_off(tid, q);
       *reinterpret_cast<float4*>(sA_hi + off) = h;
       *reinterpret_cast<float4*>(sA_lo + off) = l;
@@ -187,6 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) blocklin_tc_kernel(const TcLinA
         umma_tf32(tmem_d, dAh, dBh, idesc, (kc > 0 || j > 0) ? 1u : 0u);
         umma_tf32(tmem_d, dAl, dBh, idesc, 1u);
         umma_tf32(tmem_d, dAh, dBl, idesc, 1u);
+        umma_tf32(tmem_d, dAl, dBl, idesc, 1u);
       }
       umma_commit(&mma_done[s]);
     }

@@ -30,7 +30,10 @@ def test_tc_linear_matches_fp64(rows, K, N):
     got, ref = _dense(rows, K, N, 1, seed=rows + K)
     assert np.isfinite(got).all()
     err = np.abs(got - ref).max()
-    assert err < 3e-6 * np.sqrt(K) * max(1.0, np.abs(ref).max()), err
+    # fp32-level: a plain fp32 dot product of length K has ~1e-7 * sqrt(K) relative error
+    assert err < 4e-7 * np.sqrt(K) * max(1.0, np.abs(ref).max()), err
+    simt, _ = _dense(rows, K, N, 0, seed=rows + K) if K % 4 == 0 else (got, None)
+    assert np.abs(got - simt).max() < 6e-7 * np.sqrt(K) * max(1.0, np.abs(ref).max())
 
 
 @pytest.mark.parametrize('rows,K,N', [(300, 64, 64), (1000, 224, 224), (77, 8, 64)])
@@ -57,6 +60,8 @@ def test_engine_tc_and_simt_linears_agree():
             r = e.results()
             out[tc] = (float(r['energy'].cpu()[0]), r['forces'].cpu().numpy())
     finally:
-        set_option('tc_gemm', 1)
-    assert abs(out[0][0] - out[1][0]) < 2e-5
+        set_option('tc_gemm', 0)
+    # The tensor core accumulates with truncation: ~1e-5 eV/atom systematic energy shift on this
+    # cell (measured -8.7e-6 eV/atom), forces agree to 1e-5 eV/A.  The FP32 SIMT path is the default.
+    assert abs(out[0][0] - out[1][0]) < 64 * 2e-5
     assert np.allclose(out[0][1], out[1][1], atol=2e-5)
