@@ -47,17 +47,18 @@ def _sh_torch(lmax: int, u: torch.Tensor) -> torch.Tensor:
 
 
 class Oracle:
-    def __init__(self, meta: dict, arrays: Dict[str, np.ndarray], dtype=torch.float64):
+    def __init__(self, meta: dict, arrays: Dict[str, np.ndarray], dtype=torch.float64, device='cpu'):
         self.meta = meta
+        self.device = torch.device(device)
         self.spec: ModelSpec = build_spec(meta)
         self.dtype = dtype
-        self.w = {k: torch.as_tensor(np.asarray(v), dtype=dtype) for k, v in arrays.items()}
+        self.w = {k: torch.as_tensor(np.asarray(v), dtype=dtype, device=self.device) for k, v in arrays.items()}
         self.cg = {}
         for L in self.spec.layers:
             for p in L.paths:
                 key = (p.l1, p.l2, p.l3)
                 if key not in self.cg:
-                    self.cg[key] = torch.as_tensor(tp_path_coefficients(*key), dtype=dtype)
+                    self.cg[key] = torch.as_tensor(tp_path_coefficients(*key), dtype=dtype, device=self.device)
 
     # ---- pieces -------------------------------------------------------------------------
     def edge_embedding(self, edge_vec: torch.Tensor):
@@ -93,7 +94,7 @@ class Oracle:
         for (l, mul, _) in in_blocks:
             if l < len(out_muls):
                 fan[l] += mul
-        outs = [torch.zeros(n, out_muls[l], 2 * l + 1, dtype=x.dtype) for l in range(len(out_muls))]
+        outs = [torch.zeros(n, out_muls[l], 2 * l + 1, dtype=x.dtype, device=x.device) for l in range(len(out_muls))]
         woff = 0
         for (l, mul, off) in in_blocks:
             if l >= len(out_muls) or out_muls[l] == 0:
@@ -161,10 +162,11 @@ class Oracle:
         """species [N] species indices; edge_index [2,E] with [0]=centre i (aggregation
         target), [1]=neighbour j; edge_vec [E,3] = r_j - r_i + shift."""
         s, dt = self.spec, self.dtype
-        species_t = torch.as_tensor(np.asarray(species), dtype=torch.long)
-        dst = torch.as_tensor(np.asarray(edge_index[0]), dtype=torch.long)
-        src = torch.as_tensor(np.asarray(edge_index[1]), dtype=torch.long)
-        ev = torch.as_tensor(np.asarray(edge_vec), dtype=dt).clone().requires_grad_(True)
+        dev = self.device
+        species_t = torch.as_tensor(np.asarray(species), dtype=torch.long, device=dev)
+        dst = torch.as_tensor(np.asarray(edge_index[0]), dtype=torch.long, device=dev)
+        src = torch.as_tensor(np.asarray(edge_index[1]), dtype=torch.long, device=dev)
+        ev = torch.as_tensor(np.asarray(edge_vec), dtype=dt, device=dev).clone().requires_grad_(True)
         n = species_t.shape[0]
         saved: Dict[str, torch.Tensor] = {}
 
@@ -184,7 +186,7 @@ class Oracle:
                 saved[f'{t}.x_si1'] = x
             weight = self.radial_mlp(t, emb)
             msg = self.tensor_product(L, x[src], sh, weight)                      # convolution
-            agg = torch.zeros(n, L.dim_mid, dtype=dt).index_add_(0, dst, msg)
+            agg = torch.zeros(n, L.dim_mid, dtype=dt, device=dev).index_add_(0, dst, msg)
             agg = agg / self.w[f'{t}.den']
             if keep:
                 saved[f'{t}.weight'] = weight
@@ -215,12 +217,12 @@ class Oracle:
         else:
             fij = torch.zeros_like(ev)
         evd = ev.detach()
-        forces = torch.zeros(n, 3, dtype=dt).index_add_(0, dst, fij) \
-            - torch.zeros(n, 3, dtype=dt).index_add_(0, src, fij)
+        forces = torch.zeros(n, 3, dtype=dt, device=dev).index_add_(0, dst, fij) \
+            - torch.zeros(n, 3, dtype=dt, device=dev).index_add_(0, src, fij)
         vir = torch.stack([evd[:, 0] * fij[:, 0], evd[:, 1] * fij[:, 1], evd[:, 2] * fij[:, 2],
                            evd[:, 0] * fij[:, 1], evd[:, 1] * fij[:, 2], evd[:, 2] * fij[:, 0]],
                           dim=-1)
-        atomic_virial = -torch.zeros(n, 6, dtype=dt).index_add_(0, src, vir)
+        atomic_virial = -torch.zeros(n, 6, dtype=dt, device=dev).index_add_(0, src, vir)
         out = dict(energy=total.detach(), atomic_energy=atomic_e.detach(), forces=forces,
                    edge_force=fij, atomic_virial=atomic_virial,
                    virial=-vir.sum(0))

@@ -38,7 +38,8 @@ struct ConvArgs {
   const int4* rec;            // [E] {src, table interval, frac bits, 0}
   const float* Y;             // [E, ny_stride]  Y_1 .. Y_{NY-1} (Y_0 = 1 implicit), zero padded
   const float* x;             // [n_nodes, dim_x]
-  const float4* table;        // [knots, W/2, 2] float4: {a0e,a0o,a1e,a1o}, {a2e,a2o,a3e,a3o} per channel pair
+  const float4* table;        // [knots, W/2] {a0e,a0o,a1e,a1o}: value and slope*h of the cubic, per channel pair
+  const uint2* table23;       // [knots, W/2] {half2(a2e,a2o), half2(a3e,a3o)}: the two small cubic terms in fp16
   const float* w;             // [E, W] stored weights (operator boundary / exact-MLP mode)
   int n_dst;
   int dim_x, dim_mid, w_numel, ny_stride;

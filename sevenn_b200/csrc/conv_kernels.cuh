@@ -14,15 +14,21 @@
 // 8-byte-per-lane segment of the component-major ("cm") layout, and the node accumulators of all
 // paths stay in registers over the whole CSR row -- no atomics in the forward.
 // The radial weights w_p,u(r) come either from a cubic-Hermite table indexed by the edge length
-// (TABLE: L2-resident, [knots][W/2] x {a0,a1 | a2,a3} x {even,odd channel}) or from a stored [E, W]
+// (TABLE: L2-resident, per (knot, channel pair) {a0e,a0o,a1e,a1o} fp32 + {a2e,a2o,a3e,a3o} fp16 = 24 B)
+// or from a stored [E, W]
 // array (!TABLE: the reference's plug-in boundary, where the radial MLP stays outside).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "generated/tp_kinds.cuh"
 
 namespace s7b {
 
 constexpr int kConvWarpsPerBlock = 4;
+#ifndef S7B_PREFETCH
+#define S7B_PREFETCH 0   // measured: prefetching the next edge record costs registers and is slower (r1)
+#endif
 
 // Sum M values (M = 8 or 16) over the LPN lanes of a group with ~M-1+log2(LPN/M) shuffles instead
 // of M*log2(LPN).  On return v[0] of group-lane sl holds the total of value (sl / (LPN/M)) % M.
@@ -68,8 +74,47 @@ __device__ __forceinline__ void load_Y(const float* __restrict__ Yrow, float (&Y
 
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+// Per-lane value type: V2 = two adjacent channels (packed FFMA2 math), float = one channel.
+template <class V> struct VT;
+template <> struct VT<V2> {
+  static constexpr int CH = 2;
+  static __device__ __forceinline__ V2 zero() { return splat2(0.0f); }
+  static __device__ __forceinline__ V2 load(const float* p) { return ldg2(p); }
+  static __device__ __forceinline__ void store(float* p, V2 v) { *reinterpret_cast<float2*>(p) = v; }
+  static __device__ __forceinline__ float hsum(V2 v) { return v.x + v.y; }
+  // cubic coefficients of the channel pair starting at (even) column c of table row tk
+  static __device__ __forceinline__ void coef(const ConvArgs& a, int tk, int c, V2& a0, V2& a1, V2& a2, V2& a3) {
+    const size_t ti = (size_t)tk * (a.w_numel >> 1) + (c >> 1);
+    const float4 c01 = __ldg(a.table + ti);
+    const uint2 c23 = __ldg(a.table23 + ti);
+    a0 = make_float2(c01.x, c01.y);
+    a1 = make_float2(c01.z, c01.w);
+    a2 = __half22float2(*reinterpret_cast<const __half2*>(&c23.x));
+    a3 = __half22float2(*reinterpret_cast<const __half2*>(&c23.y));
+  }
+};
+template <> struct VT<float> {
+  static constexpr int CH = 1;
+  static __device__ __forceinline__ float zero() { return 0.0f; }
+  static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
+  static __device__ __forceinline__ float hsum(float v) { return v; }
+  static __device__ __forceinline__ void coef(const ConvArgs& a, int tk, int c, float& a0, float& a1, float& a2, float& a3) {
+    const size_t ti = (size_t)tk * (a.w_numel >> 1) + (c >> 1);
+    const float4 c01 = __ldg(a.table + ti);
+    const uint2 c23 = __ldg(a.table23 + ti);
+    const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&c23.x));
+    const float2 h3 = __half22float2(*reinterpret_cast<const __half2*>(&c23.y));
+    const bool odd = (c & 1) != 0;
+    a0 = odd ? c01.y : c01.x;
+    a1 = odd ? c01.w : c01.z;
+    a2 = odd ? h2.y : h2.x;
+    a3 = odd ? h3.y : h3.x;
+  }
+};
+
 // Which node / channel pair this lane works on.
-template <int NV, int LPN>
+template <int NV, int LPN, int CH>
 struct LaneMap {
   int n, sl, uc0, e0, len, nmax;
   bool node_ok;
@@ -79,7 +124,7 @@ struct LaneMap {
     sl = lane % LPN;
     n = (blockIdx.x * kConvWarpsPerBlock + (threadIdx.x >> 5)) * GPW + lane / LPN;
     node_ok = n < a.n_dst;
-    uc0 = blockIdx.y * (2 * LPN * NV) + 2 * sl;
+    uc0 = blockIdx.y * (CH * LPN * NV) + CH * sl;
     e0 = 0;
     len = 0;
     if (node_ok) {
@@ -95,44 +140,66 @@ struct LaneMap {
 // forward:  out[n, path block] = sum_{e in row n} w_e * CG(x[src_e], Y_e)
 // grid = (ceil(n_dst / (kConvWarpsPerBlock * 32/LPN)), mul / (2*LPN*NV)), block = 32*kConvWarpsPerBlock
 // ------------------------------------------------------------------------------------------
-template <class Kind, int NV, int LPN, bool TABLE>
+template <class Kind, int NV, int LPN, bool TABLE, class V>
 __global__ void __launch_bounds__(32 * kConvWarpsPerBlock)
 conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) {
-  const LaneMap<NV, LPN> m(a);
+  constexpr int CH = VT<V>::CH;
+  const LaneMap<NV, LPN, CH> m(a);
   if (m.nmax == 0 && !m.node_ok) return;      // whole warp beyond the last node (uniform)
 
-  V2 acc[NV][Kind::NACC];
+  V acc[NV][Kind::NACC];
 #pragma unroll
   for (int c = 0; c < NV; ++c)
 #pragma unroll
-    for (int q = 0; q < Kind::NACC; ++q) acc[c][q] = splat2(0.0f);
+    for (int q = 0; q < Kind::NACC; ++q) acc[c][q] = VT<V>::zero();
 
+  // software pipeline: the edge record and harmonics of iteration it+1 are requested before the
+  // gathers of iteration it, taking one dependent L2 round trip off the per-edge critical path
+  int4 rec_n = make_int4(0, 0, 0, 0);
+  float Y_n[Kind::NY];
+  if (m.nmax > 0) {
+    const int e = (m.len > 0) ? m.e0 : 0;
+    rec_n = __ldg(a.rec + e);
+    load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y_n);
+  }
   for (int it = 0; it < m.nmax; ++it) {
     const bool valid = (LPN == 32) || (it < m.len);
     const int e = valid ? m.e0 + it : 0;
+#if S7B_PREFETCH
+    const int4 rec = rec_n;
+    float Y[Kind::NY];
+#pragma unroll
+    for (int j = 0; j < Kind::NY; ++j) Y[j] = Y_n[j];
+#else
     const int4 rec = __ldg(a.rec + e);
     float Y[Kind::NY];
     load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y);
+#endif
+#if S7B_PREFETCH
+    if (it + 1 < m.nmax) {
+      const int en = (it + 1 < m.len) ? m.e0 + it + 1 : 0;
+      rec_n = __ldg(a.rec + en);
+      load_Y<Kind>(a.Y + (size_t)en * a.ny_stride, Y_n);
+    }
+#endif
     const float* __restrict__ xrow = a.x + (size_t)rec.x * a.dim_x + role.x_off;
     const float tt = __int_as_float(rec.z);
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
-      const int u = m.uc0 + 2 * LPN * c;
-      V2 x[Kind::D1], w[Kind::NPATH];
+      const int u = m.uc0 + CH * LPN * c;
+      V x[Kind::D1], w[Kind::NPATH];
 #pragma unroll
-      for (int i = 0; i < Kind::D1; ++i) x[i] = ldg2(xrow + i * role.mul + u);
+      for (int i = 0; i < Kind::D1; ++i) x[i] = VT<V>::load(xrow + i * role.mul + u);
 #pragma unroll
       for (int p = 0; p < Kind::NPATH; ++p) {
         if (TABLE) {
-          const float4* cp = a.table + ((size_t)rec.y * a.w_numel + role.w_off[p] + u);   // 2 float4 per pair
-          const float4 c01 = __ldg(cp), c23 = __ldg(cp + 1);
-          const V2 a0 = make_float2(c01.x, c01.y), a1 = make_float2(c01.z, c01.w);
-          const V2 a2 = make_float2(c23.x, c23.y), a3 = make_float2(c23.z, c23.w);
+          V a0, a1, a2, a3;
+          VT<V>::coef(a, rec.y, role.w_off[p] + u, a0, a1, a2, a3);
           w[p] = fma_(tt, fma_(tt, fma_(tt, a3, a2), a1), a0);
         } else {
-          w[p] = ldg2(a.w + (size_t)e * a.w_numel + role.w_off[p] + u);
+          w[p] = VT<V>::load(a.w + (size_t)e * a.w_numel + role.w_off[p] + u);
         }
-        if (LPN != 32 && !valid) w[p] = splat2(0.0f);
+        if (LPN != 32 && !valid) w[p] = VT<V>::zero();
       }
       Kind::fwd(x, Y, w, acc[c]);
     }
@@ -142,12 +209,12 @@ conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) 
   float* __restrict__ orow = out + (size_t)m.n * a.dim_mid;
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
-    const int u = m.uc0 + 2 * LPN * c;
+    const int u = m.uc0 + CH * LPN * c;
 #pragma unroll
     for (int p = 0; p < Kind::NPATH; ++p) {
 #pragma unroll
       for (int k = 0; k < 2 * Kind::path_l3(p) + 1; ++k)
-        *reinterpret_cast<float2*>(orow + role.out_off[p] + k * role.out_stride[p] + u) = acc[c][Kind::acc_off(p) + k];
+        VT<V>::store(orow + role.out_off[p] + k * role.out_stride[p] + u, acc[c][Kind::acc_off(p) + k]);
     }
   }
 }
@@ -165,7 +232,7 @@ __global__ void __launch_bounds__(32 * kConvWarpsPerBlock)
 conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__ gout,
                 float* __restrict__ dx, float* __restrict__ dY_acc, float* __restrict__ dEdr_acc,
                 float* __restrict__ dw) {
-  const LaneMap<NV, LPN> m(a);
+  const LaneMap<NV, LPN, 2> m(a);
   if (m.nmax == 0) return;                    // uniform: no edges in any row of this warp
 
   V2 ga[NV][Kind::NACC];
@@ -183,12 +250,33 @@ conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__
   }
 
   constexpr int NR = (Kind::NY <= 9) ? 8 : 16;   // values reduced with the transposing butterfly
+  int4 rec_n;
+  float Y_n[Kind::NY];
+  {
+    const int e = (m.len > 0) ? m.e0 : 0;
+    rec_n = __ldg(a.rec + e);
+    load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y_n);
+  }
   for (int it = 0; it < m.nmax; ++it) {
     const bool valid = (LPN == 32) || (it < m.len);
     const int e = valid ? m.e0 + it : 0;
+#if S7B_PREFETCH
+    const int4 rec = rec_n;
+    float Y[Kind::NY];
+#pragma unroll
+    for (int j = 0; j < Kind::NY; ++j) Y[j] = Y_n[j];
+#else
     const int4 rec = __ldg(a.rec + e);
     float Y[Kind::NY];
     load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y);
+#endif
+#if S7B_PREFETCH
+    if (it + 1 < m.nmax) {
+      const int en = (it + 1 < m.len) ? m.e0 + it + 1 : 0;
+      rec_n = __ldg(a.rec + en);
+      load_Y<Kind>(a.Y + (size_t)en * a.ny_stride, Y_n);
+    }
+#endif
     const float* __restrict__ xrow = a.x + (size_t)rec.x * a.dim_x + role.x_off;
     const float tt = __int_as_float(rec.z);
     V2 dY[Kind::NY];
@@ -204,10 +292,12 @@ conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__
 #pragma unroll
       for (int p = 0; p < Kind::NPATH; ++p) {
         if (TABLE) {
-          const float4* cp = a.table + ((size_t)rec.y * a.w_numel + role.w_off[p] + u);
-          const float4 c01 = __ldg(cp), c23 = __ldg(cp + 1);
+          const size_t ti = (size_t)rec.y * (a.w_numel >> 1) + ((role.w_off[p] + u) >> 1);
+          const float4 c01 = __ldg(a.table + ti);
+          const uint2 c23 = __ldg(a.table23 + ti);
           const V2 a0 = make_float2(c01.x, c01.y), a1 = make_float2(c01.z, c01.w);
-          const V2 a2 = make_float2(c23.x, c23.y), a3 = make_float2(c23.z, c23.w);
+          const V2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&c23.x));
+          const V2 a3 = __half22float2(*reinterpret_cast<const __half2*>(&c23.y));
           w[p] = fma_(tt, fma_(tt, fma_(tt, a3, a2), a1), a0);
           wd[p] = mul_(fma_(tt, fma_(3.0f * tt, a3, mul_(a2, 2.0f)), a1), a.inv_h);
         } else {

@@ -642,6 +642,7 @@ static ConvArgs make_conv_args(const S7bEngine* e, int t, const float* x) {
   a.Y = e->Y.as<float>();
   a.x = x;
   a.table = reinterpret_cast<const float4*>(lparam(e, t, "table"));
+  a.table23 = reinterpret_cast<const uint2*>(lparam(e, t, "table23"));
   a.w = e->desc.table_knots > 0 ? nullptr : e->wbuf[t].as<float>();
   a.n_dst = e->n_local;
   a.dim_x = L.dim_x;
@@ -720,7 +721,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         if (dense_gemm(e->h1[t].as<float>(), h0, e->h2[t].as<float>(), h1, w1, E, kEpiSiluStoreZ, nullptr, e->z2[t].as<float>(), false, st)) return 1;
         if (dense_gemm(e->h2[t].as<float>(), h1, e->wbuf[t].as<float>(), L.W, w2, E, kEpiNone, nullptr, nullptr, false, st)) return 1;
       } else if (table) {
-        if (require(lparam(e, t, "table"), "table")) return 1;
+        if (require(lparam(e, t, "table"), "table") || require(lparam(e, t, "table23"), "table23")) return 1;
       }
       // convolution: gather + tensor product + scatter (raw sums; 1/denominator is folded into si2)
       ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());

@@ -42,7 +42,7 @@ constexpr int kGemmPadM = kGemmBM + 4;
 
 // FP32 SIMT GEMM tile: 128 x 64 per CTA, 8 x 4 per thread, inner product issued as packed FFMA2
 // (scalar-broadcast A element x a pair of B columns).  grid = (ceil(max rows / BM), ceil(max N / BN), nblocks)
-__global__ void __launch_bounds__(kGemmThreads) blocklin_gemm_kernel(const LinArgs a) {
+__global__ void __launch_bounds__(kGemmThreads, 3) blocklin_gemm_kernel(const LinArgs a) {
   const LinBlock b = a.blk[blockIdx.z];
   const int rows = a.n_nodes * b.d;
   const int row0 = blockIdx.x * kGemmBM, col0 = blockIdx.y * kGemmBN;

@@ -24,7 +24,7 @@ import numpy as np
 
 from .spec import SILU_NORM, ModelSpec, build_spec
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libsevenn_b200.so')
+_LIB_PATH = os.environ.get('S7B_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libsevenn_b200.so')
 _lib = None
 
 S7B_MAX_LAYERS, S7B_MAX_L = 8, 4
@@ -163,12 +163,18 @@ def radial_table(spec: ModelSpec, arrays: Dict[str, np.ndarray], t: int, knots: 
     return np.ascontiguousarray(tab, dtype=np.float32)
 
 
-def pack_table_pairs(tab: np.ndarray) -> np.ndarray:
-    """[knots, W, 4] -> device layout [knots, W/2, 4 (coefficient), 2 (even/odd channel)]: the two
-    float4 a lane loads for its channel pair are {a0e,a0o,a1e,a1o} and {a2e,a2o,a3e,a3o}, i.e. every
-    coefficient arrives as an aligned register pair for the packed FFMA2 Horner evaluation."""
+def pack_table_pairs(tab: np.ndarray):
+    """[knots, W, 4] -> the two device arrays a lane reads for its channel pair:
+    ``table``   [knots, W/2, 4] fp32 {a0e, a0o, a1e, a1o}  (value and slope*h: need fp32)
+    ``table23`` [knots, W/2, 4] fp16 {a2e, a2o, a3e, a3o}  (|a2| <~ 1e-3, |a3| <~ 1e-5 of |w| <~ 60:
+    half precision leaves w unchanged at the fp32 rounding level and dw/dr at ~2e-7 relative rms),
+    returned bit-cast to float32 [knots, W/2, 2] for upload.  Every coefficient arrives as an aligned
+    (even, odd) pair for the packed FFMA2 Horner evaluation; 24 instead of 32 bytes per pair."""
     K, W, _ = tab.shape
-    return np.ascontiguousarray(tab.reshape(K, W // 2, 2, 4).transpose(0, 1, 3, 2))
+    pairs = tab.reshape(K, W // 2, 2, 4)                       # [k, pair, parity, coef]
+    t01 = np.ascontiguousarray(pairs[..., 0:2].transpose(0, 1, 3, 2).reshape(K, W // 2, 4), dtype=np.float32)
+    t23 = np.ascontiguousarray(pairs[..., 2:4].transpose(0, 1, 3, 2).reshape(K, W // 2, 4)).astype(np.float16)
+    return t01, np.ascontiguousarray(t23).view(np.float32)
 
 
 def default_table_knots(spec: ModelSpec) -> int:
@@ -216,7 +222,7 @@ def prepare_params(spec: ModelSpec, arrays: Dict[str, np.ndarray], radial: str, 
         out[('si2', t)] = np.concatenate([b.ravel() for b in si2])
         out[('si2T', t)] = np.concatenate([b.T.ravel() for b in si2])
         if radial == 'table':
-            out[('table', t)] = pack_table_pairs(radial_table(spec, arrays, t, knots))
+            out[('table', t)], out[('table23', t)] = pack_table_pairs(radial_table(spec, arrays, t, knots))
         else:
             for j in range(len(spec.radial_hidden) + 1):
                 W = f64(arrays[f'{t}.mlp{j}'])

@@ -74,10 +74,13 @@ def test_prepare_params_shapes_and_table_accuracy():
     P = prepare_params(spec, arrays, 'table', 500)
     assert P[('embed_x0', -1)].shape == (89, 128) and P[('embed_g0', -1)].shape == (89, 576)
     assert P[('si2', 1)].size == 86016 and P[('si1', 1)].size == 21504 and P[('sc', 4)].size == 128 * 128
-    assert P[('table', 1)].shape == (500, 480, 4, 2) and P[('readout', -1)].shape == (128,)
-    # spline vs exact radial MLP (undo the channel-pair packing first)
+    assert P[('table', 1)].shape == (500, 480, 4) and P[('table23', 1)].shape == (500, 480, 2)
+    assert P[('readout', -1)].shape == (128,)
+    # spline vs exact radial MLP (undo the channel-pair packing and the fp16 storage of a2, a3 first)
     r = np.random.RandomState(0).uniform(0.5, 4.999, 300)
-    tab = P[('table', 2)].astype(np.float64).transpose(0, 1, 3, 2).reshape(500, 960, 4)
+    t01 = P[('table', 2)].astype(np.float64).reshape(500, 480, 2, 2)             # [k, pair, coef, parity]
+    t23 = P[('table23', 2)].view(np.float16).astype(np.float64).reshape(500, 480, 2, 2)
+    tab = np.concatenate([t01, t23], axis=2).transpose(0, 1, 3, 2).reshape(500, 960, 4)
     h = spec.cutoff / 500
     k = np.minimum((r / h).astype(int), 499)
     s = (r / h - k)[:, None]
