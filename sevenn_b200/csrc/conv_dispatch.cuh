@@ -4,7 +4,8 @@
 #include "conv_kernels.cuh"
 
 #ifndef S7B_BWD_L0_NV
-#define S7B_BWD_L0_NV 1   // channel pairs per lane in the l1 = 0 backward kernels (1 measured 6% faster than 2)
+#define S7B_BWD_L0_NV 2   // channel pairs per lane in the l1 = 0 backward kernels (1 is 6% faster but splits a
+                          // (node, l1) role over two CTAs, whose per-edge dY/dE/dr sums then need atomics)
 #endif
 
 namespace s7b {
@@ -33,17 +34,25 @@ static int launch_fwd_scalar(bool table, const ConvArgs& a, const ConvRole& role
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+template <class Kind, int NV, int LPN, bool TABLE, bool NEED_DX>
+static void launch_bwd_split(const dim3& grid, const ConvArgs& a, const ConvRole& role, const float* gout,
+                             float* dx, float* dY, float* dEdr, float* dw, cudaStream_t st) {
+  const int blk = 32 * kConvWarpsPerBlock;
+  // a role split over several CTAs (grid.y > 1) accumulates its per-edge sums atomically
+  if (grid.y > 1) conv_bwd_kernel<Kind, NV, LPN, TABLE, NEED_DX, true><<<grid, blk, 0, st>>>(a, role, gout, dx, dY, dEdr, dw);
+  else conv_bwd_kernel<Kind, NV, LPN, TABLE, NEED_DX, false><<<grid, blk, 0, st>>>(a, role, gout, dx, dY, dEdr, dw);
+}
+
 template <class Kind, int NV, int LPN, bool ALLOW_NODX>
 static int launch_bwd_one(bool table, bool need_dx, const ConvArgs& a, const ConvRole& role,
                           const float* gout, float* dx, float* dY, float* dEdr, float* dw, cudaStream_t st) {
   const dim3 grid = conv_grid<LPN>(a, role, NV);
-  const int blk = 32 * kConvWarpsPerBlock;
   if (!need_dx && ALLOW_NODX) {
-    if (table) conv_bwd_kernel<Kind, NV, LPN, true, !ALLOW_NODX><<<grid, blk, 0, st>>>(a, role, gout, dx, dY, dEdr, dw);
-    else conv_bwd_kernel<Kind, NV, LPN, false, !ALLOW_NODX><<<grid, blk, 0, st>>>(a, role, gout, dx, dY, dEdr, dw);
+    if (table) launch_bwd_split<Kind, NV, LPN, true, !ALLOW_NODX>(grid, a, role, gout, dx, dY, dEdr, dw, st);
+    else launch_bwd_split<Kind, NV, LPN, false, !ALLOW_NODX>(grid, a, role, gout, dx, dY, dEdr, dw, st);
   } else {
-    if (table) conv_bwd_kernel<Kind, NV, LPN, true, true><<<grid, blk, 0, st>>>(a, role, gout, dx, dY, dEdr, dw);
-    else conv_bwd_kernel<Kind, NV, LPN, false, true><<<grid, blk, 0, st>>>(a, role, gout, dx, dY, dEdr, dw);
+    if (table) launch_bwd_split<Kind, NV, LPN, true, true>(grid, a, role, gout, dx, dY, dEdr, dw, st);
+    else launch_bwd_split<Kind, NV, LPN, false, true>(grid, a, role, gout, dx, dY, dEdr, dw, st);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

@@ -227,7 +227,7 @@ conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) 
 //   dx[src_e, :]        += dE/dx                                          (RED.ADD.F32x2, NEED_DX)
 // dY_acc / dEdr_acc / dw rows are owned by exactly one group of one launch: plain read-modify-write.
 // ------------------------------------------------------------------------------------------
-template <class Kind, int NV, int LPN, bool TABLE, bool NEED_DX>
+template <class Kind, int NV, int LPN, bool TABLE, bool NEED_DX, bool SPLIT>
 __global__ void __launch_bounds__(32 * kConvWarpsPerBlock)
 conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__ gout,
                 float* __restrict__ dx, float* __restrict__ dY_acc, float* __restrict__ dEdr_acc,
@@ -329,13 +329,24 @@ conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__
     group_reduce_multi<NR, LPN>(red, m.sl);
     constexpr int PER = LPN / NR;
     const int idx = (m.sl / PER) % NR;
+    // a (node, l1) role normally belongs to one group -> plain read-modify-write (deterministic);
+    // when its channels are split over several CTAs (gridDim.y > 1) the partial sums meet atomically
+    constexpr bool shared_rows = SPLIT;    // launched with gridDim.y > 1
     if (valid && (m.sl % PER) == 0) {
-      if (idx + 1 < Kind::NY) dY_acc[(size_t)e * a.ny_stride + idx] += red[0];
-      else if (RIDE && idx == NR - 1) dEdr_acc[e] += red[0];
+      float* p = nullptr;
+      if (idx + 1 < Kind::NY) p = dY_acc + (size_t)e * a.ny_stride + idx;
+      else if (RIDE && idx == NR - 1) p = dEdr_acc + e;
+      if (p != nullptr) {
+        if (shared_rows) atomicAdd(p, red[0]);
+        else *p += red[0];
+      }
     }
     if (TABLE && !RIDE) {
       const float s = group_sum<LPN>(dEdr);
-      if (valid && m.sl == 0) dEdr_acc[e] += s;
+      if (valid && m.sl == 0) {
+        if (shared_rows) atomicAdd(dEdr_acc + e, s);
+        else dEdr_acc[e] += s;
+      }
     }
   }
 }

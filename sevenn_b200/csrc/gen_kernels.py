@@ -163,6 +163,17 @@ def gen_kind(l1: int, lf: int, lo: int) -> str:
     return '\n'.join(out)
 
 
+def op_counts(l1: int, lf: int, lo: int):
+    """FP32 flops per (edge, channel) of the generated forward / backward bodies (fma = 2, mul/add = 1),
+    used by bench.py for the FP32-pipe fraction of the convolution kernels."""
+    import re
+    text = gen_kind(l1, lf, lo)
+    fwd = text[text.index('static void fwd('):text.index('static void bwd(')]
+    bwd = text[text.index('static void bwd('):]
+    count = lambda t: 2 * len(re.findall(r'fma_\(', t)) + len(re.findall(r'mul_\(', t)) + len(re.findall(r'add_\(', t))
+    return count(fwd), count(bwd), len(kind_paths(l1, lf, lo))
+
+
 def gen_sh(lmax: int) -> str:
     """sh_eval<L>: unit vector -> Y[1..];  sh_vjp<L>: g_c = sum_j gY[j] dY_j/du_c (c = x,y,z)."""
     import sympy as sp
