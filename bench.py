@@ -179,6 +179,10 @@ def run_engine(args):
         import datetime
         dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
 
+    from sevenn_b200.engine import set_option
+    for opt in ('concurrent_conv', 'tc_gemm'):      # A/B switches: S7B_CONCURRENT_CONV=0, S7B_TC_GEMM=1
+        if os.environ.get('S7B_' + opt.upper()) is not None:
+            set_option(opt, int(os.environ['S7B_' + opt.upper()]))
     meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{args.model}.npz'))
     tm = {int(k): int(v) for k, v in meta['type_map'].items()}
     cells = CELLS[args.gpus] if args.cells is None else tuple(args.cells)

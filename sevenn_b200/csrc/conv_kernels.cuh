@@ -330,21 +330,20 @@ conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__
     constexpr int PER = LPN / NR;
     const int idx = (m.sl / PER) % NR;
     // a (node, l1) role normally belongs to one group -> plain read-modify-write (deterministic);
-    // when its channels are split over several CTAs (gridDim.y > 1) the partial sums meet atomically
-    constexpr bool shared_rows = SPLIT;    // launched with gridDim.y > 1
+    // SPLIT (launched with gridDim.y > 1: the role's channels are spread over several CTAs) adds atomically
     if (valid && (m.sl % PER) == 0) {
-      float* p = nullptr;
-      if (idx + 1 < Kind::NY) p = dY_acc + (size_t)e * a.ny_stride + idx;
-      else if (RIDE && idx == NR - 1) p = dEdr_acc + e;
-      if (p != nullptr) {
-        if (shared_rows) atomicAdd(p, red[0]);
-        else *p += red[0];
+      if (idx + 1 < Kind::NY) {
+        if (SPLIT) atomicAdd(dY_acc + (size_t)e * a.ny_stride + idx, red[0]);
+        else dY_acc[(size_t)e * a.ny_stride + idx] += red[0];
+      } else if (RIDE && idx == NR - 1) {
+        if (SPLIT) atomicAdd(dEdr_acc + e, red[0]);
+        else dEdr_acc[e] += red[0];
       }
     }
     if (TABLE && !RIDE) {
       const float s = group_sum<LPN>(dEdr);
       if (valid && m.sl == 0) {
-        if (shared_rows) atomicAdd(dEdr_acc + e, s);
+        if (SPLIT) atomicAdd(dEdr_acc + e, s);
         else dEdr_acc[e] += s;
       }
     }

@@ -164,6 +164,11 @@ struct S7bEngine {
   DevBuf hs_species, hs_rowptr, hs_src, hs_vec;
   std::vector<int> host_rowptr;
   Profiler prof;
+  // side streams: the per-l1 convolution kernels of one layer are independent (disjoint outputs) and
+  // stress different units (l1 = 0: L1/L2 latency, l1 >= 1: FP32 pipe), so they are co-scheduled
+  cudaStream_t side[kMaxL] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxL] = {nullptr, nullptr, nullptr, nullptr};
+  bool concurrent = true;
 };
 
 struct S7bConvPlan {
@@ -276,6 +281,7 @@ static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* 
   return 0;
 }
 
+static int g_opt_concurrent = 1;   // co-schedule the per-l1 convolution kernels of a layer on side streams
 static int g_opt_tc_gemm = 0;   // 1: node linears on tcgen05 (3xTF32); default FP32 SIMT
 
 // hi = rna_tf32(w), lo = rna_tf32(w - hi)   (see tc_gemm.cuh)
@@ -441,6 +447,7 @@ int64_t s7b_launch_count(int reset) {
 int s7b_set_option(const char* name, int value) {
   if (!name) return fail("null option name");
   if (std::string(name) == "tc_gemm") { g_opt_tc_gemm = value; return 0; }
+  if (std::string(name) == "concurrent_conv") { g_opt_concurrent = value; return 0; }
   return fail(std::string("unknown option: ") + name);
 }
 
@@ -512,12 +519,28 @@ int s7b_engine_create(const S7bModelDesc* d, S7bEngine** out) {
   e->radial.n_basis = d->n_basis;
   e->radial.knots = d->table_knots > 0 ? d->table_knots : 1;
   e->radial.inv_h = d->table_knots > 0 ? (float)d->table_knots / d->cutoff : 1.0f;
+  for (int i = 1; i < kMaxL; ++i) {
+    if (cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete e;
+      return fail("cannot create side streams");
+    }
+  }
+  if (cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+    delete e;
+    return fail("cannot create events");
+  }
   *out = e;
   return 0;
 }
 
 void s7b_engine_destroy(S7bEngine* e) {
   if (!e) return;
+  for (int i = 1; i < kMaxL; ++i) {
+    if (e->side[i]) cudaStreamDestroy(e->side[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   for (auto& kv : e->params) kv.second.release();
   for (auto& L : e->layers)
     for (auto& kv : L.params) kv.second.release();
@@ -725,9 +748,19 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       }
       // convolution: gather + tensor product + scatter (raw sums; 1/denominator is folded into si2)
       ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
-      for (int l1 = 0; l1 < L.n_lx; ++l1) {
-        ProfScope ps(e->prof, st, "conv_fwd", t, l1);
-        if (launch_conv_fwd(l1, LF, L.lmax_out, table, ca, L.roles[l1], e->mid.as<float>(), st)) return 1;
+      {
+        const bool par = e->concurrent && g_opt_concurrent && !e->prof.enabled && L.n_lx > 1;
+        if (par) S7B_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
+        for (int l1 = 0; l1 < L.n_lx; ++l1) {
+          cudaStream_t s1 = (par && l1 > 0) ? e->side[l1] : st;
+          if (par && l1 > 0) S7B_CUDA_CHECK(cudaStreamWaitEvent(s1, e->ev_fork, 0));
+          ProfScope ps(e->prof, s1, "conv_fwd", t, l1);
+          if (launch_conv_fwd(l1, LF, L.lmax_out, table, ca, L.roles[l1], e->mid.as<float>(), s1)) return 1;
+          if (par && l1 > 0) {
+            S7B_CUDA_CHECK(cudaEventRecord(e->ev_join[l1], s1));
+            S7B_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join[l1], 0));
+          }
+        }
       }
       // self_interaction_2 accumulated onto the self-connection already stored in g[t]
       const float* si2 = lparam(e, t, "si2");
@@ -788,11 +821,19 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       }
       if (E > 0) {
         ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
+        const bool par = e->concurrent && g_opt_concurrent && !e->prof.enabled && L.n_lx > 1;
+        if (par) S7B_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
         for (int l1 = 0; l1 < L.n_lx; ++l1) {
           float* dY = e->dY_acc.as<float>() + (size_t)l1 * E * e->ny_stride;
           float* dEdr = e->dEdr_acc.as<float>() + (size_t)l1 * E;
-          ProfScope ps(e->prof, st, "conv_bwd", t, l1);
-          if (launch_conv_bwd(l1, LF, L.lmax_out, table, t > 0, ca, L.roles[l1], e->mid.as<float>(), e->dx.as<float>(), dY, dEdr, table ? nullptr : e->dwbuf.as<float>(), st)) return 1;
+          cudaStream_t s1 = (par && l1 > 0) ? e->side[l1] : st;
+          if (par && l1 > 0) S7B_CUDA_CHECK(cudaStreamWaitEvent(s1, e->ev_fork, 0));
+          ProfScope ps(e->prof, s1, "conv_bwd", t, l1);
+          if (launch_conv_bwd(l1, LF, L.lmax_out, table, t > 0, ca, L.roles[l1], e->mid.as<float>(), e->dx.as<float>(), dY, dEdr, table ? nullptr : e->dwbuf.as<float>(), s1)) return 1;
+          if (par && l1 > 0) {
+            S7B_CUDA_CHECK(cudaEventRecord(e->ev_join[l1], s1));
+            S7B_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join[l1], 0));
+          }
         }
         if (!table) {
           // radial MLP backward: dw -> demb (accumulated over layers)
