@@ -127,21 +127,31 @@ class GhostExchange:
             ids = recv_lists[q].cpu().numpy()
             self.send_idx.append(torch.as_tensor([gid_to_local[int(g)] for g in ids], dtype=torch.int64, device=device))
         self.bytes_per_row_exchange = sum(self.send_counts) + sum(self.recv_counts)
+        self._bufs = {}
+
+    def _sendbuf(self, q, width, dtype, device):
+        """persistent per-(peer, width) staging buffers: no allocator traffic on the step path"""
+        key = (q, width, dtype)
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = self.torch.empty((self.send_counts[q], width), dtype=dtype, device=device)
+            self._bufs[key] = buf
+        return buf
 
     def forward(self, x):
-        """x [n_nodes, D]: fill ghost rows with the owners' rows."""
+        """x [n_nodes, D]: fill ghost rows with the owners' rows (one grouped send/recv for all peers)."""
         dist, torch = self.dist, self.torch
-        ops, keep = [], []
+        ops = []
         for q in range(self.world):
             if q == self.rank:
                 continue
             if self.send_counts[q] > 0:
-                buf = x.index_select(0, self.send_idx[q])
-                keep.append(buf)
+                buf = self._sendbuf(q, x.shape[1], x.dtype, x.device)
+                torch.index_select(x, 0, self.send_idx[q], out=buf)          # pack
                 ops.append(dist.P2POp(dist.isend, buf, q, group=self.group))
             if self.recv_counts[q] > 0:
                 lo = self.n_local + int(self.recv_off[q])
-                ops.append(dist.P2POp(dist.irecv, x[lo:lo + self.recv_counts[q]], q, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, x[lo:lo + self.recv_counts[q]], q, group=self.group))  # zero-copy unpack
         if ops:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
@@ -153,11 +163,11 @@ class GhostExchange:
         for q in range(self.world):
             if q == self.rank:
                 continue
-            if self.recv_counts[q] > 0:        # my ghosts owned by q -> send their gradient rows
+            if self.recv_counts[q] > 0:        # my ghosts owned by q -> send their gradient rows (zero-copy pack)
                 lo = self.n_local + int(self.recv_off[q])
                 ops.append(dist.P2POp(dist.isend, g[lo:lo + self.recv_counts[q]], q, group=self.group))
             if self.send_counts[q] > 0:
-                buf = torch.empty((self.send_counts[q],) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+                buf = self._sendbuf(q, g.shape[1], g.dtype, g.device)
                 recvs.append((q, buf))
                 ops.append(dist.P2POp(dist.irecv, buf, q, group=self.group))
         if ops:
