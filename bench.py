@@ -265,7 +265,7 @@ def run_engine(args):
             return t, t.numpy()
         keep = [pinned(species), pinned(ei[0].astype(np.int32)), pinned(ei[1].astype(np.int32)), pinned(ev.astype(np.float32))]
         h_sp, h_c, h_n, h_v = [k[1] for k in keep]
-        h2d = h_sp.nbytes + 4 * (n_atoms + 1) + h_n.nbytes + h_v.nbytes
+        h2d = h_sp.nbytes + h_c.nbytes + h_n.nbytes + h_v.nbytes      # species, centre, neighbour, edge_vec
         d2h = 12 * n_atoms + 4 * n_atoms + 8 + 48
 
         def e2e_step():

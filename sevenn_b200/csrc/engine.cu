@@ -161,8 +161,7 @@ struct S7bEngine {
   DevBuf mid, h, dh, dg, dx, dwbuf, tmpA, tmpB;
   DevBuf energy, atomic_energy, forces, virial;
   // host staging for compute_host
-  DevBuf hs_species, hs_rowptr, hs_src, hs_vec;
-  std::vector<int> host_rowptr;
+  DevBuf hs_species, hs_rowptr, hs_src, hs_vec, hs_centre, hs_flag;
   Profiler prof;
   // side streams: the per-l1 convolution kernels of one layer are independent (disjoint outputs) and
   // stress different units (l1 = 0: L1/L2 latency, l1 >= 1: FP32 pipe), so they are co-scheduled
@@ -292,6 +291,24 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
     hi[i] = h;
     lo[i] = rna_tf32(v - h);
   }
+}
+
+// CSR over centres from a centre-sorted edge list, with validation (thread e handles the row starts
+// between centre[e-1] and centre[e]; thread n_edges closes the tail).  flag: 1 = not sorted / centre out
+// of range, 2 = neighbour out of range.
+__global__ void csr_from_sorted_kernel(const int* __restrict__ centre, const int* __restrict__ neighbour,
+                                       int64_t n_edges, int n_nodes, int* __restrict__ rowptr,
+                                       int* __restrict__ flag) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > n_edges) return;
+  const int prev = (e == 0) ? -1 : centre[e - 1];
+  const int cur = (e == n_edges) ? n_nodes : centre[e];
+  if (e < n_edges) {
+    if (cur < prev || cur < 0 || cur >= n_nodes) { atomicOr(flag, 1); return; }
+    const int nb = neighbour[e];
+    if (nb < 0 || nb >= n_nodes) atomicOr(flag, 2);
+  }
+  for (int c = max(prev, -1) + 1; c <= min(cur, n_nodes); ++c) rowptr[c] = (int)e;
 }
 
 // out[n, k] = in[k, n]
@@ -547,7 +564,7 @@ void s7b_engine_destroy(S7bEngine* e) {
   DevBuf* bufs[] = {&e->rec, &e->Y, &e->rlen, &e->emb, &e->dY_acc, &e->dEdr_acc, &e->demb_acc, &e->fedge,
                     &e->mid, &e->h, &e->dh, &e->dg, &e->dx, &e->dwbuf, &e->tmpA, &e->tmpB, &e->energy,
                     &e->atomic_energy, &e->forces, &e->virial, &e->hs_species, &e->hs_rowptr, &e->hs_src,
-                    &e->hs_vec};
+                    &e->hs_vec, &e->hs_centre, &e->hs_flag};
   for (DevBuf* b : bufs) b->release();
   for (auto* v : {&e->x, &e->g, &e->wbuf, &e->z1, &e->z2, &e->h1, &e->h2})
     for (auto& b : *v) b.release();
@@ -964,26 +981,29 @@ int s7b_engine_compute_host(S7bEngine* e, int32_t n_nodes, int64_t n_edges, cons
   if (n_nodes > 0 && !species) return fail("null species");
   if (n_edges > 0 && (!edge_centre || !edge_neighbour || !edge_vec)) return fail("null edge arrays");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // CSR over centres; the caller promises centre-major order (as pair_e3gnn.cpp:136-170 emits)
-  e->host_rowptr.assign((size_t)n_nodes + 1, 0);
-  int prev = 0;
-  for (int64_t k = 0; k < n_edges; ++k) {
-    const int c = edge_centre[k];
-    if (c < prev || c >= n_nodes) return fail("edges must be sorted by centre and centres must be < n_nodes");
-    if (edge_neighbour[k] < 0 || edge_neighbour[k] >= n_nodes) return fail("edge neighbour index out of range");
-    prev = c;
-    e->host_rowptr[(size_t)c + 1]++;
-  }
-  for (int i = 0; i < n_nodes; ++i) e->host_rowptr[(size_t)i + 1] += e->host_rowptr[i];
+  // H2D of the caller's arrays; the CSR over centres is built (and the edge list validated) on the
+  // device.  The caller promises centre-major order, as pair_e3gnn.cpp:136-170 emits.
   const size_t E = (size_t)std::max<int64_t>(n_edges, 1), N = (size_t)std::max(n_nodes, 1);
   if (e->hs_species.ensure(N * sizeof(int)) || e->hs_rowptr.ensure((N + 1) * sizeof(int)) ||
-      e->hs_src.ensure(E * sizeof(int)) || e->hs_vec.ensure(E * 3 * sizeof(float)))
+      e->hs_src.ensure(E * sizeof(int)) || e->hs_vec.ensure(E * 3 * sizeof(float)) ||
+      e->hs_centre.ensure(E * sizeof(int)) || e->hs_flag.ensure(sizeof(int)))
     return fail("cudaMalloc failed for staging buffers");
   if (n_nodes > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_species.p, species, (size_t)n_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
-  S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_rowptr.p, e->host_rowptr.data(), ((size_t)n_nodes + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  S7B_CUDA_CHECK(cudaMemsetAsync(e->hs_flag.p, 0, sizeof(int), st));
   if (n_edges > 0) {
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_centre.p, edge_centre, (size_t)n_edges * sizeof(int), cudaMemcpyHostToDevice, st));
     S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_src.p, edge_neighbour, (size_t)n_edges * sizeof(int), cudaMemcpyHostToDevice, st));
     S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_vec.p, edge_vec, (size_t)n_edges * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  {
+    const int64_t nthreads = n_edges + 1;
+    csr_from_sorted_kernel<<<(int)((nthreads + 255) / 256), 256, 0, st>>>(e->hs_centre.as<int>(), e->hs_src.as<int>(), n_edges, n_nodes, e->hs_rowptr.as<int>(), e->hs_flag.as<int>());
+    S7B_LAUNCH_CHECK();
+    int flag = 0;
+    S7B_CUDA_CHECK(cudaMemcpyAsync(&flag, e->hs_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    S7B_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (flag & 1) return fail("edges must be sorted by centre and centres must be < n_nodes");
+    if (flag & 2) return fail("edge neighbour index out of range");
   }
   if (s7b_engine_set_graph(e, n_nodes, n_nodes, n_edges, e->hs_species.as<int>(), e->hs_rowptr.as<int>(), e->hs_src.as<int>(), e->hs_vec.as<float>(), stream)) return 1;
   if (s7b_engine_compute(e, stream)) return 1;
