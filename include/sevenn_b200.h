@@ -118,6 +118,21 @@ S7B_API int s7b_engine_compute_host(S7bEngine* eng, int32_t n_nodes, int64_t n_e
                             const int32_t* edge_neighbour, const float* edge_vec, double* energy,
                             float* atomic_energy, float* forces, double* virial, void* stream);
 
+/* Positions in: builds the neighbour list / CSR graph on the device (cell list over the
+ * fractional cell, any cell size and shape, per-direction pbc) with the semantics of the reference's
+ * graph builder (sevenn/train/dataload.py:32-129: every image pair with |r_j - r_i + S.cell| < cutoff,
+ * edge_vec in double -> float) and makes it the engine's current graph.  positions [n,3] and cell
+ * [3,3] (rows = lattice vectors) are host doubles, pbc3 host ints.  The compute variant then runs all
+ * stages and copies energy / forces [n,3] / virial back; *n_edges_out receives the edge count. */
+S7B_API int s7b_engine_set_positions_host(S7bEngine* eng, int32_t n_atoms, const int32_t* species,
+                                          const double* positions, const double* cell9, const int32_t* pbc3,
+                                          void* stream);
+S7B_API int s7b_engine_compute_positions_host(S7bEngine* eng, int32_t n_atoms, const int32_t* species,
+                                              const double* positions, const double* cell9,
+                                              const int32_t* pbc3, double* energy, float* atomic_energy,
+                                              float* forces, double* virial, int64_t* n_edges_out,
+                                              void* stream);
+
 /* Per-kernel timing with CUDA events recorded on the launching stream around every kernel (or
  * kernel group) of the stage sequence; labels like "conv_bwd.t2.l1".  Enable, run steps, then read. */
 S7B_API int s7b_engine_set_profiling(S7bEngine* eng, int enable);

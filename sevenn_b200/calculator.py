@@ -17,7 +17,6 @@ import numpy as np
 
 from .checkpoint import convert_reference_checkpoint, load_weights
 from .engine import B200Engine
-from .neighbors import build_graph
 
 _WEIGHTS_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'weights')
 # names the reference resolves in sevenn/util.py:264-312
@@ -108,18 +107,15 @@ class SevenNetCalculator(_Base):
             species = np.array([self.type_map[int(z)] for z in numbers], dtype=np.int32)
         except KeyError as e:  # same failure mode as sequential.py:131-137 for unknown elements
             raise ValueError(f'atomic number {e} is not known to this model') from None
-        ei, ev = build_graph(pos, cell, pbc, self.cutoff)
-        self.engine.set_graph(species, ei, ev)
-        self.engine.compute()
-        res = self.engine.results()
-        energy = float(res['energy'].cpu()[0])
+        # neighbour list, graph build, model and force path all run on the GPU (one C-ABI call);
+        # the reference builds the graph on the CPU every step (calculator.py:224-226)
+        energy, energies, forces, virial, n_edges = self.engine.compute_positions(species, pos, cell, pbc)
         vol = abs(np.linalg.det(cell)) if pbc.all() else 0.0
-        virial = res['virial'].cpu().numpy()
         self.results = {
             'free_energy': energy, 'energy': energy,
-            'energies': res['atomic_energy'].cpu().numpy().astype(np.float64),
-            'forces': res['forces'].cpu().numpy().astype(np.float64),
-            'num_edges': int(ei.shape[1]),
+            'energies': energies.astype(np.float64),
+            'forces': forces.astype(np.float64),
+            'num_edges': n_edges,
         }
         if vol > 0:
             inferred_stress = virial / vol

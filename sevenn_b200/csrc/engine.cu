@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "conv_kernels.cuh"
 #include "edge_kernels.cuh"
+#include "neighbor.cuh"
 #include "node_kernels.cuh"
 #include "tc_gemm.cuh"
 
@@ -162,6 +163,8 @@ struct S7bEngine {
   DevBuf energy, atomic_energy, forces, virial;
   // host staging for compute_host
   DevBuf hs_species, hs_rowptr, hs_src, hs_vec, hs_centre, hs_flag;
+  // device neighbour list (positions -> CSR)
+  DevBuf nl_pos, nl_wrapped, nl_key, nl_key_sorted, nl_idx, nl_idx_sorted, nl_bin_start, nl_count, nl_tmp;
   Profiler prof;
   // side streams: the per-l1 convolution kernels of one layer are independent (disjoint outputs) and
   // stress different units (l1 = 0: L1/L2 latency, l1 >= 1: FP32 pipe), so they are co-scheduled
@@ -564,7 +567,8 @@ void s7b_engine_destroy(S7bEngine* e) {
   DevBuf* bufs[] = {&e->rec, &e->Y, &e->rlen, &e->emb, &e->dY_acc, &e->dEdr_acc, &e->demb_acc, &e->fedge,
                     &e->mid, &e->h, &e->dh, &e->dg, &e->dx, &e->dwbuf, &e->tmpA, &e->tmpB, &e->energy,
                     &e->atomic_energy, &e->forces, &e->virial, &e->hs_species, &e->hs_rowptr, &e->hs_src,
-                    &e->hs_vec, &e->hs_centre, &e->hs_flag};
+                    &e->hs_vec, &e->hs_centre, &e->hs_flag, &e->nl_pos, &e->nl_wrapped, &e->nl_key, &e->nl_key_sorted,
+                    &e->nl_idx, &e->nl_idx_sorted, &e->nl_bin_start, &e->nl_count, &e->nl_tmp};
   for (DevBuf* b : bufs) b->release();
   for (auto* v : {&e->x, &e->g, &e->wbuf, &e->z1, &e->z2, &e->h1, &e->h2})
     for (auto& b : *v) b.release();
@@ -964,6 +968,9 @@ void* s7b_engine_buffer(S7bEngine* e, const char* name, int layer, size_t* numel
   else if (nm == "edge_force") { p = e->fedge.p; n = (size_t)e->n_edges * 3; }
   else if (nm == "edge_Y") { p = e->Y.p; n = (size_t)e->n_edges * e->ny_stride; }
   else if (nm == "edge_rec") { p = e->rec.p; n = (size_t)e->n_edges * 4; }
+  else if (nm == "graph_rowptr") { p = (void*)e->d_rowptr; n = (size_t)e->n_local + 1; }
+  else if (nm == "graph_src") { p = (void*)e->d_src; n = (size_t)e->n_edges; }
+  else if (nm == "graph_edge_vec") { p = (void*)e->d_edge_vec; n = (size_t)e->n_edges * 3; }
   else if (nm == "edge_len") { p = e->rlen.p; n = (size_t)e->n_edges; }
   else if (nm == "edge_emb") { p = e->emb.p; n = (size_t)e->n_edges * e->desc.n_basis; }
   else if (nm == "dY_acc") { p = e->dY_acc.p; n = (size_t)e->n_edges * e->ny_stride; }
@@ -1011,6 +1018,132 @@ int s7b_engine_compute_host(S7bEngine* e, int32_t n_nodes, int64_t n_edges, cons
   if (virial) S7B_CUDA_CHECK(cudaMemcpyAsync(virial, e->virial.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (atomic_energy && n_nodes > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(atomic_energy, e->atomic_energy.p, (size_t)n_nodes * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (forces && n_nodes > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(forces, e->forces.p, (size_t)n_nodes * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  S7B_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- positions in: device neighbour list + graph build ------------------------
+static int invert3(const double* m, double* inv) {
+  const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+  if (fabs(det) < 1e-12) return 1;
+  const double id = 1.0 / det;
+  inv[0] = (m[4] * m[8] - m[5] * m[7]) * id; inv[1] = (m[2] * m[7] - m[1] * m[8]) * id; inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  inv[3] = (m[5] * m[6] - m[3] * m[8]) * id; inv[4] = (m[0] * m[8] - m[2] * m[6]) * id; inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  inv[6] = (m[3] * m[7] - m[4] * m[6]) * id; inv[7] = (m[1] * m[6] - m[0] * m[7]) * id; inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return 0;
+}
+
+int s7b_engine_set_positions_host(S7bEngine* e, int32_t n_atoms, const int32_t* species, const double* positions,
+                                  const double* cell9, const int32_t* pbc3, void* stream) {
+  if (!e) return fail("null engine");
+  if (n_atoms < 0 || (n_atoms > 0 && (!species || !positions))) return fail("bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  NLGrid g;
+  memset(&g, 0, sizeof(g));
+  const double cutoff = (double)e->desc.cutoff;
+  g.cutoff2 = cutoff * cutoff;
+  for (int a = 0; a < 3; ++a) g.pbc[a] = (pbc3 && pbc3[a]) ? 1 : 0;
+  for (int k = 0; k < 9; ++k) g.cell[k] = cell9 ? cell9[k] : 0.0;
+  for (int a = 0; a < 3; ++a) {      // complete missing lattice vectors of non-periodic directions
+    const double* v = g.cell + 3 * a;
+    if (v[0] * v[0] + v[1] * v[1] + v[2] * v[2] < 1e-20) {
+      if (g.pbc[a]) return fail("periodic direction with a zero lattice vector");
+      g.cell[3 * a + a] = 1.0;
+    }
+  }
+  if (invert3(g.cell, g.inv)) return fail("singular cell");
+  // plane spacings
+  double height[3];
+  for (int a = 0; a < 3; ++a) {      // |row a of inv^T| = 1 / height_a
+    const double nx = g.inv[0 * 3 + a], ny = g.inv[1 * 3 + a], nz = g.inv[2 * 3 + a];
+    height[a] = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+  }
+  // fractional bounding range of non-periodic directions (host pass over the caller's positions)
+  for (int a = 0; a < 3; ++a) { g.fmin[a] = 0.0; g.fspan[a] = 1.0; }
+  if (!(g.pbc[0] && g.pbc[1] && g.pbc[2]) && n_atoms > 0) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n_atoms; ++i)
+      for (int a = 0; a < 3; ++a) {
+        const double f = positions[3 * i] * g.inv[0 * 3 + a] + positions[3 * i + 1] * g.inv[1 * 3 + a] + positions[3 * i + 2] * g.inv[2 * 3 + a];
+        lo[a] = std::min(lo[a], f);
+        hi[a] = std::max(hi[a], f);
+      }
+    for (int a = 0; a < 3; ++a)
+      if (!g.pbc[a]) { g.fmin[a] = lo[a]; g.fspan[a] = std::max(hi[a] - lo[a], 1e-9) * (1.0 + 1e-9); }
+  }
+  long long nbins = 1;
+  for (int a = 0; a < 3; ++a) {
+    const double extent = height[a] * g.fspan[a];
+    int nb = (int)floor(extent / cutoff);
+    nb = std::max(1, std::min(nb, 512));
+    g.nb[a] = nb;
+    g.R[a] = g.pbc[a] ? (int)ceil(cutoff / (extent / nb) - 1e-12) : std::min(nb - 1, (int)ceil(cutoff / (extent / nb) - 1e-12));
+    if (g.R[a] < 0) g.R[a] = 0;
+    nbins *= nb;
+  }
+  if (nbins > (1LL << 26)) return fail("neighbour grid too large");
+  const size_t N = (size_t)std::max(n_atoms, 1);
+  int rc = 0;
+  rc |= e->hs_species.ensure(N * sizeof(int));
+  rc |= e->hs_rowptr.ensure((N + 1) * sizeof(int));
+  rc |= e->nl_pos.ensure(N * 3 * sizeof(double));
+  rc |= e->nl_wrapped.ensure(N * 3 * sizeof(double));
+  rc |= e->nl_key.ensure(N * sizeof(int));
+  rc |= e->nl_key_sorted.ensure(N * sizeof(int));
+  rc |= e->nl_idx.ensure(N * sizeof(int));
+  rc |= e->nl_idx_sorted.ensure(N * sizeof(int));
+  rc |= e->nl_bin_start.ensure(((size_t)nbins + 1) * sizeof(int));
+  rc |= e->nl_count.ensure((N + 1) * sizeof(int));
+  if (rc) return fail("cudaMalloc failed for the neighbour list");
+  int64_t n_edges = 0;
+  if (n_atoms > 0) {
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_species.p, species, (size_t)n_atoms * sizeof(int), cudaMemcpyHostToDevice, st));
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->nl_pos.p, positions, (size_t)n_atoms * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int blk = 128, grd = (n_atoms + blk - 1) / blk;
+    nl_bin_kernel<<<grd, blk, 0, st>>>(g, e->nl_pos.as<double>(), n_atoms, e->nl_key.as<int>(), e->nl_idx.as<int>(), e->nl_wrapped.as<double>());
+    S7B_LAUNCH_CHECK();
+    size_t tmp_sort = 0, tmp_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, e->nl_key.as<int>(), e->nl_key_sorted.as<int>(), e->nl_idx.as<int>(), e->nl_idx_sorted.as<int>(), n_atoms, 0, 32, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, e->nl_count.as<int>(), e->hs_rowptr.as<int>(), n_atoms + 1, st);
+    if (e->nl_tmp.ensure(std::max(tmp_sort, tmp_scan) + 256)) return fail("cudaMalloc failed for cub workspace");
+    size_t tmp = e->nl_tmp.bytes;
+    S7B_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(e->nl_tmp.p, tmp, e->nl_key.as<int>(), e->nl_key_sorted.as<int>(), e->nl_idx.as<int>(), e->nl_idx_sorted.as<int>(), n_atoms, 0, 32, st));
+    ++g_launches;
+    nl_bin_start_kernel<<<(n_atoms + 1 + 255) / 256, 256, 0, st>>>(e->nl_key_sorted.as<int>(), n_atoms, (int)nbins, e->nl_bin_start.as<int>());
+    S7B_LAUNCH_CHECK();
+    S7B_CUDA_CHECK(cudaMemsetAsync(e->nl_count.p, 0, ((size_t)n_atoms + 1) * sizeof(int), st));
+    nl_pairs_kernel<false><<<grd, blk, 0, st>>>(g, e->nl_wrapped.as<double>(), e->nl_key.as<int>(), e->nl_idx_sorted.as<int>(), e->nl_bin_start.as<int>(), n_atoms, e->nl_count.as<int>(), nullptr, nullptr, nullptr);
+    S7B_LAUNCH_CHECK();
+    tmp = e->nl_tmp.bytes;
+    S7B_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(e->nl_tmp.p, tmp, e->nl_count.as<int>(), e->hs_rowptr.as<int>(), n_atoms + 1, st));
+    ++g_launches;
+    int total = 0;
+    S7B_CUDA_CHECK(cudaMemcpyAsync(&total, e->hs_rowptr.as<int>() + n_atoms, sizeof(int), cudaMemcpyDeviceToHost, st));
+    S7B_CUDA_CHECK(cudaStreamSynchronize(st));
+    n_edges = total;
+    const size_t E = (size_t)std::max<int64_t>(n_edges, 1);
+    if (e->hs_src.ensure(E * sizeof(int)) || e->hs_vec.ensure(E * 3 * sizeof(float))) return fail("cudaMalloc failed for the edge list");
+    if (n_edges > 0) {
+      nl_pairs_kernel<true><<<grd, blk, 0, st>>>(g, e->nl_wrapped.as<double>(), e->nl_key.as<int>(), e->nl_idx_sorted.as<int>(), e->nl_bin_start.as<int>(), n_atoms, nullptr, e->hs_rowptr.as<int>(), e->hs_src.as<int>(), e->hs_vec.as<float>());
+      S7B_LAUNCH_CHECK();
+    }
+  } else {
+    S7B_CUDA_CHECK(cudaMemsetAsync(e->hs_rowptr.p, 0, sizeof(int), st));
+  }
+  return s7b_engine_set_graph(e, n_atoms, n_atoms, n_edges, e->hs_species.as<int>(), e->hs_rowptr.as<int>(), e->hs_src.as<int>(), e->hs_vec.as<float>(), stream);
+}
+
+int s7b_engine_compute_positions_host(S7bEngine* e, int32_t n_atoms, const int32_t* species, const double* positions,
+                                      const double* cell9, const int32_t* pbc3, double* energy, float* atomic_energy,
+                                      float* forces, double* virial, int64_t* n_edges_out, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (s7b_engine_set_positions_host(e, n_atoms, species, positions, cell9, pbc3, stream)) return 1;
+  if (n_edges_out) *n_edges_out = e->n_edges;
+  if (s7b_engine_compute(e, stream)) return 1;
+  if (energy) S7B_CUDA_CHECK(cudaMemcpyAsync(energy, e->energy.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (virial) S7B_CUDA_CHECK(cudaMemcpyAsync(virial, e->virial.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (atomic_energy && n_atoms > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(atomic_energy, e->atomic_energy.p, (size_t)n_atoms * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (forces && n_atoms > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(forces, e->forces.p, (size_t)n_atoms * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   S7B_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }

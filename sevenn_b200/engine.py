@@ -48,7 +48,8 @@ class S7bModelDesc(ctypes.Structure):
 EXPORTS = [
     's7b_last_error', 's7b_version', 's7b_set_option', 's7b_dense_linear', 's7b_engine_create', 's7b_engine_destroy',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
-    's7b_engine_buffer', 's7b_engine_compute_host', 's7b_launch_count', 's7b_engine_set_profiling',
+    's7b_engine_buffer', 's7b_engine_compute_host', 's7b_engine_set_positions_host',
+    's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_set_profiling',
     's7b_engine_profile_count', 's7b_engine_profile_entry', 's7b_conv_plan_create',
     's7b_conv_plan_destroy', 's7b_conv_plan_dims', 's7b_conv_forward', 's7b_conv_backward',
 ]
@@ -78,6 +79,8 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_engine_buffer.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(sz)]
     lib.s7b_engine_buffer.restype = vp
     lib.s7b_engine_compute_host.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.s7b_engine_set_positions_host.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.s7b_engine_compute_positions_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.s7b_engine_set_profiling.argtypes = [vp, ctypes.c_int]
     lib.s7b_engine_profile_count.argtypes = [vp]
     lib.s7b_engine_profile_entry.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, sz,
@@ -389,6 +392,51 @@ class B200Engine:
         self.n_nodes = self.n_local = n
         self.n_edges = E
         return float(energy[0]), ae, forces, virial
+
+    @staticmethod
+    def _pos_args(species, positions, cell, pbc):
+        sp = np.ascontiguousarray(species, dtype=np.int32)
+        pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        c = np.zeros((3, 3)) if cell is None else np.ascontiguousarray(cell, dtype=np.float64).reshape(3, 3)
+        pb = np.ascontiguousarray(np.broadcast_to(np.asarray(pbc, dtype=bool), (3,)).astype(np.int32))
+        return sp, pos, np.ascontiguousarray(c), pb
+
+    def set_positions(self, species, positions, cell, pbc):
+        """Build the neighbour list / graph on the device from host positions (C ABI
+        ``s7b_engine_set_positions_host``) and make it the current graph."""
+        sp, pos, c, pb = self._pos_args(species, positions, cell, pbc)
+        with self.torch.cuda.device(self.device):
+            check(self.lib.s7b_engine_set_positions_host(self._h, len(sp), sp.ctypes.data, pos.ctypes.data,
+                                                         c.ctypes.data, pb.ctypes.data, self._stream()))
+        self._graph = dict(perm=None)
+        self.n_nodes = self.n_local = len(sp)
+        n = ctypes.c_size_t()
+        self.lib.s7b_engine_buffer(self._h, b'graph_src', 0, ctypes.byref(n))
+        self.n_edges = int(n.value)
+        return self
+
+    def graph_arrays(self):
+        """(rowptr, src, edge_vec) of the current graph as torch views."""
+        return (self.buffer('graph_rowptr', dtype='i4', shape=(self.n_local + 1,)),
+                self.buffer('graph_src', dtype='i4', shape=(self.n_edges,)),
+                self.buffer('graph_edge_vec', shape=(self.n_edges, 3)))
+
+    def compute_positions(self, species, positions, cell, pbc):
+        """positions in -> (energy, atomic_energy, forces, virial6, n_edges): neighbour list, all stages
+        and the copies back in one C-ABI call (``s7b_engine_compute_positions_host``)."""
+        sp, pos, c, pb = self._pos_args(species, positions, cell, pbc)
+        n = len(sp)
+        energy, virial = np.zeros(1, np.float64), np.zeros(6, np.float64)
+        ae, forces = np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+        ne = ctypes.c_int64()
+        with self.torch.cuda.device(self.device):
+            check(self.lib.s7b_engine_compute_positions_host(
+                self._h, n, sp.ctypes.data, pos.ctypes.data, c.ctypes.data, pb.ctypes.data, energy.ctypes.data,
+                ae.ctypes.data, forces.ctypes.data, virial.ctypes.data, ctypes.byref(ne), self._stream()))
+        self._graph = dict(perm=None)
+        self.n_nodes = self.n_local = n
+        self.n_edges = int(ne.value)
+        return float(energy[0]), ae, forces, virial, int(ne.value)
 
     def set_profiling(self, enable: bool):
         check(self.lib.s7b_engine_set_profiling(self._h, 1 if enable else 0))
