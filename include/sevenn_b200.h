@@ -69,7 +69,15 @@ enum {
   S7B_STAGE_FWD_END = 2,
   S7B_STAGE_BWD_LAYER_A = 3,
   S7B_STAGE_BWD_LAYER_B = 4,
-  S7B_STAGE_BWD_END = 5
+  S7B_STAGE_BWD_END = 5,
+  /* finer split for comm/compute overlap (FWD_LAYER = FWD_LAYER_A + FWD_LAYER_SC, BWD_LAYER_B = B1 + B2):
+   * FWD_LAYER_A(t) ends with the local rows of x(t+1); the self-connection GEMM FWD_LAYER_SC(t) does not
+   * need the ghost rows and can run while they are exchanged.  BWD_LAYER_B1(t) (self-connection term of
+   * dE/dh) does not need the reverse exchange of dx(t); BWD_LAYER_B2(t) adds the dx term afterwards. */
+  S7B_STAGE_FWD_LAYER_A = 6,
+  S7B_STAGE_FWD_LAYER_SC = 7,
+  S7B_STAGE_BWD_LAYER_B1 = 8,
+  S7B_STAGE_BWD_LAYER_B2 = 9
 };
 
 S7B_API const char* s7b_last_error(void);

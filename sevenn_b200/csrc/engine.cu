@@ -751,7 +751,8 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       }
       return 0;
     }
-    case S7B_STAGE_FWD_LAYER: {
+    case S7B_STAGE_FWD_LAYER:
+    case S7B_STAGE_FWD_LAYER_A: {
       if (t < 0 || t >= T) return fail("layer out of range");
       const LayerCfg& L = e->layers[t];
       if (Nl == 0) return 0;
@@ -798,16 +799,27 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       }
       if (t + 1 < T) {
         const LayerCfg& N = e->layers[t + 1];
-        const float *si1 = lparam(e, t + 1, "si1"), *sc = lparam(e, t + 1, "sc");
-        if (require(si1, "si1") || require(sc, "sc")) return 1;
-        ProfScope ps(e->prof, st, "si1_sc_gemm", t + 1);
-        // self_interaction_1 of the next layer -> local rows of x[t+1]
+        const float* si1 = lparam(e, t + 1, "si1");
+        if (require(si1, "si1")) return 1;
+        ProfScope ps(e->prof, st, "si1_gemm", t + 1);
+        // self_interaction_1 of the next layer -> local rows of x[t+1] (ghost rows: caller's exchange)
         if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st, lparam(e, t + 1, "si1T.hi"), lparam(e, t + 1, "si1T.lo"))) return 1;
-        // self_connection_intro of the next layer -> initial value of g[t+1]
-        S7B_CUDA_CHECK(cudaMemsetAsync(e->g[t + 1].p, 0, (size_t)Nl * N.dim_g * sizeof(float), st));
-        const int n_sc = std::min(N.n_lx, N.n_lg);
-        if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->g[t + 1].as<float>(), N.dim_g, N.g_off, N.g_muls, n_sc, sc, Nl, false, st, lparam(e, t + 1, "scT.hi"), lparam(e, t + 1, "scT.lo"))) return 1;
       }
+      if (stage == S7B_STAGE_FWD_LAYER_A) return 0;
+    }
+    // fall through: FWD_LAYER = FWD_LAYER_A + FWD_LAYER_SC
+    case S7B_STAGE_FWD_LAYER_SC: {
+      if (t < 0 || t >= T) return fail("layer out of range");
+      if (Nl == 0 || t + 1 >= T) return 0;
+      const LayerCfg& N = e->layers[t + 1];
+      const float* sc = lparam(e, t + 1, "sc");
+      if (require(sc, "sc")) return 1;
+      ProfScope ps(e->prof, st, "sc_gemm", t + 1);
+      // self_connection_intro of the next layer -> initial value of g[t+1]; independent of the ghost
+      // exchange of x[t+1], so multi-GPU callers overlap the two
+      S7B_CUDA_CHECK(cudaMemsetAsync(e->g[t + 1].p, 0, (size_t)Nl * N.dim_g * sizeof(float), st));
+      const int n_sc = std::min(N.n_lx, N.n_lg);
+      if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->g[t + 1].as<float>(), N.dim_g, N.g_off, N.g_muls, n_sc, sc, Nl, false, st, lparam(e, t + 1, "scT.hi"), lparam(e, t + 1, "scT.lo"))) return 1;
       return 0;
     }
     case S7B_STAGE_FWD_END: {
@@ -869,17 +881,25 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       }
       return 0;
     }
-    case S7B_STAGE_BWD_LAYER_B: {
+    case S7B_STAGE_BWD_LAYER_B:
+    case S7B_STAGE_BWD_LAYER_B1:
+    case S7B_STAGE_BWD_LAYER_B2: {
       if (t <= 0 || t >= T) return fail("BWD_LAYER_B needs 1 <= layer < n_layers");
       const LayerCfg& L = e->layers[t];
       if (Nl == 0) return 0;
       const float *si1T = lparam(e, t, "si1T"), *scT = lparam(e, t, "scT");
       if (require(si1T, "si1T") || require(scT, "scT")) return 1;
-      // dE/dh(t) = dx(t) * si1^T + dg(t) * sc^T     (h(t) = gate output of layer t-1)
+      // dE/dh(t) = dg(t) * sc^T + dx(t) * si1^T     (h(t) = gate output of layer t-1).  B1 (the self-
+      // connection term) does not need the reverse ghost exchange of dx and can overlap it; B2 adds the rest.
       ProfScope ps(e->prof, st, "si1T_scT_gemm", t);
-      if (irreps_linear(e->dx.as<float>(), L.dim_x, L.x_off, L.x_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, L.n_lx, si1T, Nl, false, st, lparam(e, t, "si1.hi"), lparam(e, t, "si1.lo"))) return 1;
-      const int n_sc = std::min(L.n_lx, L.n_lg);
-      if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, n_sc, scT, Nl, true, st, lparam(e, t, "sc.hi"), lparam(e, t, "sc.lo"))) return 1;
+      if (stage != S7B_STAGE_BWD_LAYER_B2) {
+        const int n_sc = std::min(L.n_lx, L.n_lg);
+        S7B_CUDA_CHECK(cudaMemsetAsync(e->dh.p, 0, (size_t)Nl * L.dim_x * sizeof(float), st));
+        if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, n_sc, scT, Nl, false, st, lparam(e, t, "sc.hi"), lparam(e, t, "sc.lo"))) return 1;
+      }
+      if (stage != S7B_STAGE_BWD_LAYER_B1) {
+        if (irreps_linear(e->dx.as<float>(), L.dim_x, L.x_off, L.x_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, L.n_lx, si1T, Nl, true, st, lparam(e, t, "si1.hi"), lparam(e, t, "si1.lo"))) return 1;
+      }
       return 0;
     }
     case S7B_STAGE_BWD_END: {

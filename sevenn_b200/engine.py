@@ -29,7 +29,7 @@ _lib = None
 
 S7B_MAX_LAYERS, S7B_MAX_L = 8, 4
 (STAGE_FWD_BEGIN, STAGE_FWD_LAYER, STAGE_FWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B,
- STAGE_BWD_END) = range(6)
+ STAGE_BWD_END, STAGE_FWD_LAYER_A, STAGE_FWD_LAYER_SC, STAGE_BWD_LAYER_B1, STAGE_BWD_LAYER_B2) = range(10)
 
 
 class S7bModelDesc(ctypes.Structure):

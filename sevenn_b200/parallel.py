@@ -27,8 +27,9 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from .engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B, STAGE_FWD_BEGIN,
-                     STAGE_FWD_END, STAGE_FWD_LAYER)
+from .engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B, STAGE_BWD_LAYER_B1,
+                     STAGE_BWD_LAYER_B2, STAGE_FWD_BEGIN, STAGE_FWD_END, STAGE_FWD_LAYER,
+                     STAGE_FWD_LAYER_A, STAGE_FWD_LAYER_SC)
 
 
 def owner_of(frac: np.ndarray, grid: Sequence[int]) -> np.ndarray:
@@ -126,55 +127,60 @@ class GhostExchange:
                 continue
             ids = recv_lists[q].cpu().numpy()
             self.send_idx.append(torch.as_tensor([gid_to_local[int(g)] for g in ids], dtype=torch.int64, device=device))
-        self.bytes_per_row_exchange = sum(self.send_counts) + sum(self.recv_counts)
+        self.send_counts[self.rank] = 0
+        self.n_ghost = int(sum(self.recv_counts))
+        self.send_idx_all = torch.cat(self.send_idx) if self.world > 0 else torch.zeros(0, dtype=torch.int64, device=device)
         self._bufs = {}
 
-    def _sendbuf(self, q, width, dtype, device):
-        """persistent per-(peer, width) staging buffers: no allocator traffic on the step path"""
-        key = (q, width, dtype)
+    def _packed(self, width, dtype, device):
+        """persistent [sum(send_counts), width] staging buffer: no allocator traffic on the step path"""
+        key = (width, dtype)
         buf = self._bufs.get(key)
         if buf is None:
-            buf = self.torch.empty((self.send_counts[q], width), dtype=dtype, device=device)
+            buf = self.torch.empty((sum(self.send_counts), width), dtype=dtype, device=device)
             self._bufs[key] = buf
         return buf
 
-    def forward(self, x):
-        """x [n_nodes, D]: fill ghost rows with the owners' rows (one grouped send/recv for all peers)."""
-        dist, torch = self.dist, self.torch
-        ops = []
+    def forward(self, x, async_op=False):
+        """x [n_nodes, D]: fill ghost rows with the owners' rows.  One gather kernel packs the rows for
+        all peers (ordered by destination rank), one all-to-all-v (NCCL grouped send/recv) delivers them
+        straight into the ghost rows of x, which are ordered by source rank (zero-copy unpack)."""
+        if self.n_ghost == 0 and sum(self.send_counts) == 0:
+            return None
+        packed = self._packed(x.shape[1], x.dtype, x.device)
+        if packed.shape[0] > 0:
+            self.torch.index_select(x, 0, self.send_idx_all, out=packed)
+        return self.dist.all_to_all_single(x[self.n_local:self.n_local + self.n_ghost], packed,
+                                           output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
+                                           group=self.group, async_op=async_op)
+
+    def reverse_begin(self, g):
+        """start sending the ghost rows of g to their owners (zero-copy pack); returns a handle"""
+        if self.n_ghost == 0 and sum(self.send_counts) == 0:
+            return None
+        packed = self._packed(g.shape[1], g.dtype, g.device)
+        work = self.dist.all_to_all_single(packed, g[self.n_local:self.n_local + self.n_ghost],
+                                           output_split_sizes=self.send_counts, input_split_sizes=self.recv_counts,
+                                           group=self.group, async_op=True)
+        return (work, packed, g)
+
+    def reverse_finish(self, handle):
+        """wait, then add the received rows peer by peer in rank order (indices are unique within one
+        peer's slice), so the sums are deterministic"""
+        if handle is None:
+            return
+        work, packed, g = handle
+        work.wait()
+        off = 0
         for q in range(self.world):
-            if q == self.rank:
-                continue
-            if self.send_counts[q] > 0:
-                buf = self._sendbuf(q, x.shape[1], x.dtype, x.device)
-                torch.index_select(x, 0, self.send_idx[q], out=buf)          # pack
-                ops.append(dist.P2POp(dist.isend, buf, q, group=self.group))
-            if self.recv_counts[q] > 0:
-                lo = self.n_local + int(self.recv_off[q])
-                ops.append(dist.P2POp(dist.irecv, x[lo:lo + self.recv_counts[q]], q, group=self.group))  # zero-copy unpack
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            c = self.send_counts[q]
+            if c > 0:
+                g.index_add_(0, self.send_idx[q], packed[off:off + c])
+            off += c
 
     def reverse_add(self, g):
         """g [n_nodes, D]: add every ghost row into its owner's row (sum over all ranks)."""
-        dist, torch = self.dist, self.torch
-        ops, recvs = [], []
-        for q in range(self.world):
-            if q == self.rank:
-                continue
-            if self.recv_counts[q] > 0:        # my ghosts owned by q -> send their gradient rows (zero-copy pack)
-                lo = self.n_local + int(self.recv_off[q])
-                ops.append(dist.P2POp(dist.isend, g[lo:lo + self.recv_counts[q]], q, group=self.group))
-            if self.send_counts[q] > 0:
-                buf = self._sendbuf(q, g.shape[1], g.dtype, g.device)
-                recvs.append((q, buf))
-                ops.append(dist.P2POp(dist.irecv, buf, q, group=self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for q, buf in recvs:                   # fixed peer order -> deterministic sums
-            g.index_add_(0, self.send_idx[q], buf)
+        self.reverse_finish(self.reverse_begin(g))
 
 
 class DistributedRunner:
@@ -201,15 +207,21 @@ class DistributedRunner:
         spec = eng.spec
         eng.run_stage(STAGE_FWD_BEGIN)
         for t in range(T):
-            eng.run_stage(STAGE_FWD_LAYER, t)
-            if t + 1 < T:
-                self.exchange.forward(self._buf('x', t + 1, spec.layers[t + 1].dim_x))
+            eng.run_stage(STAGE_FWD_LAYER_A, t)
+            work = None
+            if t + 1 < T:       # ghost rows of x(t+1) travel while the self-connection GEMM runs
+                work = self.exchange.forward(self._buf('x', t + 1, spec.layers[t + 1].dim_x), async_op=True)
+            eng.run_stage(STAGE_FWD_LAYER_SC, t)
+            if work is not None:
+                work.wait()
         eng.run_stage(STAGE_FWD_END)
         for t in range(T - 1, -1, -1):
             eng.run_stage(STAGE_BWD_LAYER_A, t)
-            if t > 0:
-                self.exchange.reverse_add(self._buf('dx', t, spec.layers[t].dim_x))
-                eng.run_stage(STAGE_BWD_LAYER_B, t)
+            if t > 0:           # ghost rows of dx(t) travel back while the self-connection term is computed
+                handle = self.exchange.reverse_begin(self._buf('dx', t, spec.layers[t].dim_x))
+                eng.run_stage(STAGE_BWD_LAYER_B1, t)
+                self.exchange.reverse_finish(handle)
+                eng.run_stage(STAGE_BWD_LAYER_B2, t)
         eng.run_stage(STAGE_BWD_END)
         forces = eng.buffer('forces', shape=(self.n_nodes, 3))
         self.exchange.reverse_add(forces)

@@ -11,8 +11,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sevenn_b200.engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B, STAGE_FWD_BEGIN,
-                                STAGE_FWD_END, STAGE_FWD_LAYER)
+from sevenn_b200.engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B, STAGE_BWD_LAYER_B1,
+                                STAGE_BWD_LAYER_B2, STAGE_FWD_BEGIN, STAGE_FWD_END, STAGE_FWD_LAYER,
+                                STAGE_FWD_LAYER_A, STAGE_FWD_LAYER_SC)
 from sevenn_b200.neighbors import build_graph, diamond_si, rocksalt_nacl
 from sevenn_b200.parallel import DistributedRunner, brick_decompose
 
@@ -64,7 +65,9 @@ class FakeEngine:
         if stage == STAGE_FWD_BEGIN:
             self.x[0][:] = (self.species + 1.0)[:, None]
             self.dEdw.zero_()
-        elif stage == STAGE_FWD_LAYER:
+        elif stage in (STAGE_FWD_LAYER_SC, STAGE_BWD_LAYER_B1):
+            pass        # the stand-in has no self-connection term
+        elif stage in (STAGE_FWD_LAYER, STAGE_FWD_LAYER_A):
             a = torch.zeros(nl, self.D, dtype=torch.float64).index_add_(0, self.dst, self.w[:, None] * self.x[t][self.src])
             self.a[t] = a
             self.h = torch.tanh(a)
@@ -79,7 +82,7 @@ class FakeEngine:
             self.dx.zero_()
             if t > 0:
                 self.dx.index_add_(0, self.src, self.w[:, None] * da[self.dst])
-        elif stage == STAGE_BWD_LAYER_B:
+        elif stage in (STAGE_BWD_LAYER_B, STAGE_BWD_LAYER_B2):
             self.dh = self.coef[t - 1] * self.dx[:nl]
         elif stage == STAGE_BWD_END:
             f = self.dEdw[:, None] * self.vec / self.w[:, None]
