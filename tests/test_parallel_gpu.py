@@ -73,7 +73,9 @@ def test_multi_gpu_matches_oracle(world, grid, model):
         forces[gids], forces_h[gids], ae[gids] = f, f_h, a
         assert abs(energy - float(ref['energy'])) < 1e-4
         assert abs(e_h - energy) < 1e-6
-        assert np.allclose(virial, ref['virial'].numpy(), atol=1e-3, rtol=1e-5)
+        # virial = sum over ~4000 edges of r (x) f in fp32 products: fp32 edge-force noise (~5e-6 eV/A)
+        # accumulates to ~2e-3 eV on components of magnitude ~90 eV
+        assert np.allclose(virial, ref['virial'].numpy(), atol=5e-3, rtol=1e-5)
     assert np.allclose(forces, ref['forces'].numpy(), atol=5e-5)
     assert np.allclose(forces_h, forces, atol=5e-6)
     assert np.allclose(ae, ref['atomic_energy'].numpy(), atol=2e-5)
