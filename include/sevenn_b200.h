@@ -85,7 +85,9 @@ S7B_API int s7b_version(void);
 
 /* Runtime options: "tc_gemm" = 1 runs the node linears on tcgen05 tensor cores (3xTF32 with TMEM
  * accumulators; ~5e-7 relative error with a small systematic component from the tensor core's
- * truncating accumulation); 0 (default) selects the FP32 SIMT GEMM kernel (IEEE fp32 FMA chain). */
+ * truncating accumulation); 0 (default) selects the FP32 SIMT GEMM kernel (IEEE fp32 FMA chain).
+ * "atomic_virial" = 1: engines created afterwards also fill the buffer "atomic_virial" [n_nodes, 6]
+ * (force_output.py:198-214).  "concurrent_conv" (default 1): co-schedule the per-l1 convolution kernels. */
 S7B_API int s7b_set_option(const char* name, int value);
 
 /* C[rows, N] = A[rows, K] * W[K, N] (row-major, device pointers) through the same GEMM kernels the

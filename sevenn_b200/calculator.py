@@ -89,7 +89,8 @@ class SevenNetCalculator(_Base):
             raise RuntimeError('sevenn_b200 has no CPU path; pass a CUDA device')
         self.meta, self.arrays = resolve_model(model) if isinstance(model, str) else model
         self.engine = B200Engine(self.meta, self.arrays, radial=radial,
-                                 device=dev.index if dev.index is not None else None)
+                                 device=dev.index if dev.index is not None else None,
+                                 atomic_virial=compute_atomic_virial)
         self.cutoff = self.engine.spec.cutoff
         self.type_map = self.engine.spec.type_map
         self.compute_atomic_virial = compute_atomic_virial
@@ -120,4 +121,6 @@ class SevenNetCalculator(_Base):
         if vol > 0:
             inferred_stress = virial / vol
             self.results['stress'] = -inferred_stress[[0, 1, 2, 4, 5, 3]]
+        if self.compute_atomic_virial:   # calculator.py:211-216: 'stresses' = the per-atom virial as the model gives it
+            self.results['stresses'] = self.engine.buffer('atomic_virial', shape=(len(numbers), 6)).cpu().numpy().astype(np.float64)
         return self.results

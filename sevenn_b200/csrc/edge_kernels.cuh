@@ -121,11 +121,13 @@ __global__ void edge_bwd_kernel(const RadialDesc rd, const float* __restrict__ e
 
 // forces[i] = sum_{e: dst = i} f_e - sum_{e: src = i} f_e   (force_output.py:189-195)
 // virial6   = -sum_e (r_x f_x, r_y f_y, r_z f_z, r_x f_y, r_y f_z, r_z f_x)   (:198-228, before / V)
+// atomic_virial (optional, [n_nodes, 6]) = -(per-edge 6-vector scattered onto the neighbour), :198-214.
 // One warp per centre atom for the CSR part; the neighbour part uses RED.ADD.
 __global__ void force_scatter_kernel(const int* __restrict__ rowptr, const int* __restrict__ src,
                                      const float* __restrict__ edge_vec,
                                      const float* __restrict__ fedge, int n_dst,
-                                     float* __restrict__ forces, double* __restrict__ virial) {
+                                     float* __restrict__ forces, double* __restrict__ virial,
+                                     float* __restrict__ atomic_virial) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   float fx = 0.f, fy = 0.f, fz = 0.f;
@@ -140,8 +142,13 @@ __global__ void force_scatter_kernel(const int* __restrict__ rowptr, const int* 
       atomicAdd(forces + 3 * (size_t)s + 0, -ax);
       atomicAdd(forces + 3 * (size_t)s + 1, -ay);
       atomicAdd(forces + 3 * (size_t)s + 2, -az);
-      v[0] += rx * ax; v[1] += ry * ay; v[2] += rz * az;
-      v[3] += rx * ay; v[4] += ry * az; v[5] += rz * ax;
+      const float w6[6] = {rx * ax, ry * ay, rz * az, rx * ay, ry * az, rz * ax};
+#pragma unroll
+      for (int q = 0; q < 6; ++q) v[q] += w6[q];
+      if (atomic_virial != nullptr) {      // per-atom virial lives on the neighbour atom, negated
+#pragma unroll
+        for (int q = 0; q < 6; ++q) atomicAdd(atomic_virial + 6 * (size_t)s + q, -w6[q]);
+      }
     }
   }
 #pragma unroll

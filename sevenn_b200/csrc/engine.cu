@@ -160,7 +160,8 @@ struct S7bEngine {
   DevBuf rec, Y, rlen, emb, dY_acc, dEdr_acc, demb_acc, fedge;
   std::vector<DevBuf> x, g, wbuf, z1, z2, h1, h2;   // per layer (wbuf.. exact-MLP mode only)
   DevBuf mid, h, dh, dg, dx, dwbuf, tmpA, tmpB;
-  DevBuf energy, atomic_energy, forces, virial;
+  DevBuf energy, atomic_energy, forces, virial, atomic_virial;
+  bool want_atomic_virial = false;
   // host staging for compute_host
   DevBuf hs_species, hs_rowptr, hs_src, hs_vec, hs_centre, hs_flag;
   // device neighbour list (positions -> CSR)
@@ -283,6 +284,7 @@ static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* 
   return 0;
 }
 
+static int g_opt_atomic_virial = 0;   // engines created afterwards also produce the per-atom virial
 static int g_opt_concurrent = 1;   // co-schedule the per-l1 convolution kernels of a layer on side streams
 static int g_opt_tc_gemm = 0;   // 1: node linears on tcgen05 (3xTF32); default FP32 SIMT
 
@@ -467,6 +469,7 @@ int64_t s7b_launch_count(int reset) {
 int s7b_set_option(const char* name, int value) {
   if (!name) return fail("null option name");
   if (std::string(name) == "tc_gemm") { g_opt_tc_gemm = value; return 0; }
+  if (std::string(name) == "atomic_virial") { g_opt_atomic_virial = value; return 0; }
   if (std::string(name) == "concurrent_conv") { g_opt_concurrent = value; return 0; }
   return fail(std::string("unknown option: ") + name);
 }
@@ -539,6 +542,7 @@ int s7b_engine_create(const S7bModelDesc* d, S7bEngine** out) {
   e->radial.n_basis = d->n_basis;
   e->radial.knots = d->table_knots > 0 ? d->table_knots : 1;
   e->radial.inv_h = d->table_knots > 0 ? (float)d->table_knots / d->cutoff : 1.0f;
+  e->want_atomic_virial = g_opt_atomic_virial != 0;
   for (int i = 1; i < kMaxL; ++i) {
     if (cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
@@ -566,7 +570,7 @@ void s7b_engine_destroy(S7bEngine* e) {
     for (auto& kv : L.params) kv.second.release();
   DevBuf* bufs[] = {&e->rec, &e->Y, &e->rlen, &e->emb, &e->dY_acc, &e->dEdr_acc, &e->demb_acc, &e->fedge,
                     &e->mid, &e->h, &e->dh, &e->dg, &e->dx, &e->dwbuf, &e->tmpA, &e->tmpB, &e->energy,
-                    &e->atomic_energy, &e->forces, &e->virial, &e->hs_species, &e->hs_rowptr, &e->hs_src,
+                    &e->atomic_energy, &e->forces, &e->virial, &e->atomic_virial, &e->hs_species, &e->hs_rowptr, &e->hs_src,
                     &e->hs_vec, &e->hs_centre, &e->hs_flag, &e->nl_pos, &e->nl_wrapped, &e->nl_key, &e->nl_key_sorted,
                     &e->nl_idx, &e->nl_idx_sorted, &e->nl_bin_start, &e->nl_count, &e->nl_tmp};
   for (DevBuf* b : bufs) b->release();
@@ -673,6 +677,7 @@ int s7b_engine_set_graph(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t
   rc |= e->virial.ensure(6 * sizeof(double));
   rc |= e->atomic_energy.ensure(Nl * sizeof(float));
   rc |= e->forces.ensure(Nn * 3 * sizeof(float));
+  if (e->want_atomic_virial) rc |= e->atomic_virial.ensure(Nn * 6 * sizeof(float));
   if (rc) return fail("cudaMalloc failed while sizing step buffers");
   return 0;
 }
@@ -905,6 +910,8 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
     case S7B_STAGE_BWD_END: {
       S7B_CUDA_CHECK(cudaMemsetAsync(e->forces.p, 0, (size_t)std::max(Nn, 1) * 3 * sizeof(float), st));
       S7B_CUDA_CHECK(cudaMemsetAsync(e->virial.p, 0, 6 * sizeof(double), st));
+      const bool av = e->want_atomic_virial && e->atomic_virial.p != nullptr;
+      if (av) S7B_CUDA_CHECK(cudaMemsetAsync(e->atomic_virial.p, 0, (size_t)std::max(Nn, 1) * 6 * sizeof(float), st));
       if (E > 0 && Nl > 0) {
         const int blk = 256;
         const int grd = (int)((E + blk - 1) / blk);
@@ -917,7 +924,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         else if (LF == 2) edge_bwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
         else edge_bwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
         S7B_LAUNCH_CHECK();
-        force_scatter_kernel<<<(Nl * 32 + blk - 1) / blk, blk, 0, st>>>(e->d_rowptr, e->d_src, e->d_edge_vec, e->fedge.as<float>(), Nl, e->forces.as<float>(), e->virial.as<double>());
+        force_scatter_kernel<<<(Nl * 32 + blk - 1) / blk, blk, 0, st>>>(e->d_rowptr, e->d_src, e->d_edge_vec, e->fedge.as<float>(), Nl, e->forces.as<float>(), e->virial.as<double>(), av ? e->atomic_virial.as<float>() : nullptr);
         S7B_LAUNCH_CHECK();
       }
       return 0;
@@ -984,6 +991,7 @@ void* s7b_engine_buffer(S7bEngine* e, const char* name, int layer, size_t* numel
   else if (nm == "energy") { p = e->energy.p; n = 1; }
   else if (nm == "virial") { p = e->virial.p; n = 6; }
   else if (nm == "atomic_energy") { p = e->atomic_energy.p; n = (size_t)e->n_local; }
+  else if (nm == "atomic_virial" && e->want_atomic_virial) { p = e->atomic_virial.p; n = (size_t)e->n_nodes * 6; }
   else if (nm == "forces") { p = e->forces.p; n = (size_t)e->n_nodes * 3; }
   else if (nm == "edge_force") { p = e->fedge.p; n = (size_t)e->n_edges * 3; }
   else if (nm == "edge_Y") { p = e->Y.p; n = (size_t)e->n_edges * e->ny_stride; }

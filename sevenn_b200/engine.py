@@ -255,7 +255,7 @@ class B200Engine:
     (the radial MLP evaluated exactly per edge with FP32 GEMM kernels)."""
 
     def __init__(self, meta: dict, arrays: Dict[str, np.ndarray], radial: str = 'table',
-                 knots: Optional[int] = None, device: Optional[int] = None):
+                 knots: Optional[int] = None, device: Optional[int] = None, atomic_virial: bool = False):
         import torch
         if not torch.cuda.is_available():
             raise RuntimeError('sevenn_b200 needs a CUDA device (sm_100a); there is no CPU path')
@@ -283,8 +283,11 @@ class B200Engine:
                 d.muls[t][l] = m
         d.table_knots = self.knots
         self._h = ctypes.c_void_p()
+        self.atomic_virial = bool(atomic_virial)
         with torch.cuda.device(self.device):
+            set_option('atomic_virial', 1 if atomic_virial else 0)
             check(self.lib.s7b_engine_create(ctypes.byref(d), ctypes.byref(self._h)))
+            set_option('atomic_virial', 0)
             for (name, t), arr in prepare_params(spec, arrays, radial, self.knots).items():
                 check(self.lib.s7b_engine_set_param(self._h, name.encode(), t, arr.ctypes.data, arr.size))
         self._graph = None

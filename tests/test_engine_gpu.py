@@ -197,3 +197,25 @@ def test_calculator_surface(engines):
     assert np.allclose(res['energies'], g['energies'], atol=1e-5)
     assert np.allclose(res['stress'], g['ase_stress'], atol=1e-5)
     assert res['num_edges'] == 58
+
+
+def test_atomic_virial_matches_oracle():
+    """compute_atomic_virial=True: 'stresses' = per-atom virial (force_output.py:198-214), and it sums to
+    the total virial."""
+    from sevenn_b200.calculator import SevenNetCalculator
+    g = golden_vectors()['7net0_hfo2_0']
+
+    class Atoms:
+        def get_positions(s): return np.array(g['system']['positions'])
+        def get_cell(s): return np.array(g['system']['cell'])
+        def get_pbc(s): return np.array([True] * 3)
+        def get_atomic_numbers(s): return np.array(g['system']['numbers'])
+
+    calc = SevenNetCalculator('7net-0', device='cuda', compute_atomic_virial=True)
+    res = calc.calculate(Atoms())
+    meta, _ = model_weights('sevennet_0')
+    ei, ev, vol = system_graph(g['system'], 5.0)
+    ref = oracle('sevennet_0').forward(species_of(meta, g['system']['numbers']), ei, ev, volume=vol)
+    assert np.allclose(res['stresses'], ref['atomic_virial'].numpy(), atol=5e-5)
+    assert np.allclose(res['stresses'].sum(0) / vol, -res['stress'][[0, 1, 2, 5, 3, 4]], atol=1e-6)
+    assert np.allclose(res['energies'], g['energies'], atol=2e-5) and np.allclose(res['forces'], g['forces'], atol=3e-5)
