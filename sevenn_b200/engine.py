@@ -242,6 +242,24 @@ def prepare_params(spec: ModelSpec, arrays: Dict[str, np.ndarray], radial: str, 
     return {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in out.items()}
 
 
+def model_desc(spec: ModelSpec, knots: int) -> S7bModelDesc:
+    """The C struct ``S7bModelDesc`` (include/sevenn_b200.h) for a model spec."""
+    d = S7bModelDesc()
+    d.n_layers, d.lmax_filter, d.num_species, d.n_basis = spec.n_layers, spec.lmax_filter, spec.num_species, spec.n_basis
+    d.cutoff, d.cutoff_fn = spec.cutoff, 0 if spec.cutoff_fn == 'XPLOR' else 1
+    d.cutoff_on, d.poly_p = spec.cutoff_on, spec.poly_p
+    if len(spec.radial_hidden) != 2:
+        raise NotImplementedError('radial MLP must have two hidden layers')
+    d.radial_hidden[0], d.radial_hidden[1] = spec.radial_hidden
+    irreps = [list(L.x_muls) for L in spec.layers] + [list(spec.layers[-1].out_muls)]
+    for t, muls in enumerate(irreps):
+        d.n_l[t] = len(muls)
+        for l, m in enumerate(muls):
+            d.muls[t][l] = m
+    d.table_knots = knots
+    return d
+
+
 class _DevView:
     """``__cuda_array_interface__`` view of an engine-owned device buffer."""
 
@@ -269,19 +287,7 @@ class B200Engine:
         self.radial = radial
         self.knots = (knots or default_table_knots(self.spec)) if radial == 'table' else 0
         spec = self.spec
-        d = S7bModelDesc()
-        d.n_layers, d.lmax_filter, d.num_species, d.n_basis = spec.n_layers, spec.lmax_filter, spec.num_species, spec.n_basis
-        d.cutoff, d.cutoff_fn = spec.cutoff, 0 if spec.cutoff_fn == 'XPLOR' else 1
-        d.cutoff_on, d.poly_p = spec.cutoff_on, spec.poly_p
-        if len(spec.radial_hidden) != 2:
-            raise NotImplementedError('radial MLP must have two hidden layers')
-        d.radial_hidden[0], d.radial_hidden[1] = spec.radial_hidden
-        irreps = [list(L.x_muls) for L in spec.layers] + [list(spec.layers[-1].out_muls)]
-        for t, muls in enumerate(irreps):
-            d.n_l[t] = len(muls)
-            for l, m in enumerate(muls):
-                d.muls[t][l] = m
-        d.table_knots = self.knots
+        d = model_desc(spec, self.knots)
         self._h = ctypes.c_void_p()
         self.atomic_virial = bool(atomic_virial)
         with torch.cuda.device(self.device):

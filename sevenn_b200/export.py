@@ -12,28 +12,12 @@ radial tables packed), i.e. exactly what ``s7b_engine_set_param`` takes.
 """
 from __future__ import annotations
 
-import ctypes
 import struct
 
 import numpy as np
 
-from .engine import S7bModelDesc, default_table_knots, prepare_params
+from .engine import default_table_knots, model_desc, prepare_params
 from .spec import build_spec
-
-
-def model_desc(spec, knots: int) -> S7bModelDesc:
-    d = S7bModelDesc()
-    d.n_layers, d.lmax_filter, d.num_species, d.n_basis = spec.n_layers, spec.lmax_filter, spec.num_species, spec.n_basis
-    d.cutoff, d.cutoff_fn = spec.cutoff, 0 if spec.cutoff_fn == 'XPLOR' else 1
-    d.cutoff_on, d.poly_p = spec.cutoff_on, spec.poly_p
-    d.radial_hidden[0], d.radial_hidden[1] = spec.radial_hidden
-    irreps = [list(L.x_muls) for L in spec.layers] + [list(spec.layers[-1].out_muls)]
-    for t, muls in enumerate(irreps):
-        d.n_l[t] = len(muls)
-        for l, m in enumerate(muls):
-            d.muls[t][l] = m
-    d.table_knots = knots
-    return d
 
 
 def export_flat(path: str, meta: dict, arrays, radial: str = 'table', knots=None) -> None:
