@@ -180,7 +180,7 @@ def run_engine(args):
         dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     from sevenn_b200.engine import set_option
-    for opt in ('concurrent_conv', 'tc_gemm'):      # A/B switches: S7B_CONCURRENT_CONV=0, S7B_TC_GEMM=1
+    for opt in ('concurrent_conv', 'tc_gemm', 'cuda_graph'):   # A/B switches: S7B_CONCURRENT_CONV=0, S7B_TC_GEMM=1, S7B_CUDA_GRAPH=0
         if os.environ.get('S7B_' + opt.upper()) is not None:
             set_option(opt, int(os.environ['S7B_' + opt.upper()]))
     meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{args.model}.npz'))
@@ -318,6 +318,7 @@ def run_engine(args):
                 'weights': f'{args.model} converted from the reference checkpoint', 'radial': args.radial,
                 'parallelism': 'single GPU' if world == 1 else f'spatial bricks {GRIDS[args.gpus]} + NCCL ghost exchange',
                 'l2': 'flushed with a 256 MiB write between timed steps',
+                'cuda_graph': bool(int(os.environ.get('S7B_CUDA_GRAPH', '1'))) and world == 1 and args.radial == 'table',
                 'energy_eV': float(out[0]) if world == 1 else float(out['energy'])},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'e2e_positions': e2e_pos,

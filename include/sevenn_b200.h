@@ -87,7 +87,10 @@ S7B_API int s7b_version(void);
  * accumulators; ~5e-7 relative error with a small systematic component from the tensor core's
  * truncating accumulation); 0 (default) selects the FP32 SIMT GEMM kernel (IEEE fp32 FMA chain).
  * "atomic_virial" = 1: engines created afterwards also fill the buffer "atomic_virial" [n_nodes, 6]
- * (force_output.py:198-214).  "concurrent_conv" (default 1): co-schedule the per-l1 convolution kernels. */
+ * (force_output.py:198-214).  "concurrent_conv" (default 1): co-schedule the per-l1 convolution kernels.
+ * "cuda_graph" (default 1): s7b_engine_compute (and the two *_host entry points built on it) replay a
+ * captured CUDA graph of the step instead of issuing its ~75 launches; recaptured automatically when
+ * sizes, edge capacity, graph pointers or allocations change. */
 S7B_API int s7b_set_option(const char* name, int value);
 
 /* C[rows, N] = A[rows, K] * W[K, N] (row-major, device pointers) through the same GEMM kernels the
@@ -150,8 +153,12 @@ S7B_API int s7b_engine_profile_count(S7bEngine* eng);
 S7B_API int s7b_engine_profile_entry(S7bEngine* eng, int index, char* name, size_t name_len,
                                      double* total_ms, int64_t* calls);
 
-/* Number of kernels this library launched since the last reset (bench.py's gpu_launches). */
+/* Number of kernels this library launched since the last reset (bench.py's gpu_launches); kernels run
+ * by a CUDA-graph replay are counted per replay. */
 S7B_API int64_t s7b_launch_count(int reset);
+
+/* How often s7b_engine_compute captured a new CUDA graph / replayed one (either pointer may be NULL). */
+S7B_API int s7b_engine_graph_stats(S7bEngine* eng, int64_t* captures, int64_t* replays);
 
 /* ---- operator-level plug-in: fused gather -> 'uvu' tensor product -> scatter ------------- */
 /* irreps of x as multiplicities per l (even parity), filter lmax, and lmax of the output; the

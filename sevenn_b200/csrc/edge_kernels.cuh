@@ -44,13 +44,15 @@ S7B_HD void envelope(const RadialDesc& d, float r, float& env, float& denv) {
 
 // One thread per edge.  Writes rec = {src, interval, frac, 0}, Y[e, 0..ny_stride) = Y_1.., r, and
 // (exact-MLP mode) the radial embedding emb[e, 0..n_basis).
+// The edge count is read from device memory and the grid is sized for the engine's edge capacity, so
+// a captured CUDA graph of the step stays valid when the neighbour count changes between MD steps.
 template <int LMAX>
 __global__ void edge_fwd_kernel(const RadialDesc rd, const float* __restrict__ edge_vec,
-                                const int* __restrict__ src, int64_t n_edges, int ny_stride,
+                                const int* __restrict__ src, const int64_t* __restrict__ n_edges_p, int ny_stride,
                                 int4* __restrict__ rec, float* __restrict__ Yout,
                                 float* __restrict__ rlen, float* __restrict__ emb) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
+  if (e >= *n_edges_p) return;
   const float vx = edge_vec[3 * e], vy = edge_vec[3 * e + 1], vz = edge_vec[3 * e + 2];
   const float r = sqrtf(vx * vx + vy * vy + vz * vz);
   const float ir = 1.0f / r;
@@ -76,14 +78,15 @@ __global__ void edge_fwd_kernel(const RadialDesc rd, const float* __restrict__ e
 
 // One thread per edge: total dE/d(edge_vec) from the accumulated per-l1 partials.
 //   f = (dE/dr) r^ + (1/r) (I - r^ r^T) J_Y^T (dE/dY)
-// dY_acc: [n_part, E, ny_stride], dEdr_acc: [n_part, E]; demb (optional, exact-MLP mode): [E, n_basis]
+// dY_acc: [n_part, part_stride, ny_stride], dEdr_acc: [n_part, part_stride] (part_stride = edge
+// capacity >= E); demb (optional, exact-MLP mode): [E, n_basis]
 template <int LMAX>
 __global__ void edge_bwd_kernel(const RadialDesc rd, const float* __restrict__ edge_vec,
-                                int64_t n_edges, int ny_stride, int n_part,
+                                const int64_t* __restrict__ n_edges_p, int64_t part_stride, int ny_stride, int n_part,
                                 const float* __restrict__ dY_acc, const float* __restrict__ dEdr_acc,
                                 const float* __restrict__ demb, float* __restrict__ fedge) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
+  if (e >= *n_edges_p) return;
   const float vx = edge_vec[3 * e], vy = edge_vec[3 * e + 1], vz = edge_vec[3 * e + 2];
   const float r = sqrtf(vx * vx + vy * vy + vz * vz);
   const float ir = 1.0f / r;
@@ -94,10 +97,10 @@ __global__ void edge_bwd_kernel(const RadialDesc rd, const float* __restrict__ e
   for (int j = 1; j < SH<LMAX>::NY; ++j) gY[j] = 0.0f;
   float gr = 0.0f;
   for (int p = 0; p < n_part; ++p) {
-    const float* row = dY_acc + ((size_t)p * n_edges + e) * ny_stride;
+    const float* row = dY_acc + ((size_t)p * part_stride + e) * ny_stride;
 #pragma unroll
     for (int j = 1; j < SH<LMAX>::NY; ++j) gY[j] += row[j - 1];
-    if (dEdr_acc != nullptr) gr += dEdr_acc[(size_t)p * n_edges + e];
+    if (dEdr_acc != nullptr) gr += dEdr_acc[(size_t)p * part_stride + e];
   }
   if (demb != nullptr) {
     float env, denv;

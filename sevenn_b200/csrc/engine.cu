@@ -51,11 +51,14 @@ int launch_conv_bwd(int l1, int lf, int lo, bool table, bool need_dx, const Conv
                     const ConvRole& role, const float* gout, float* dx, float* dY_acc,
                     float* dEdr_acc, float* dw, cudaStream_t st);
 
+static int64_t g_alloc_gen = 0;   // bumped by every (re)allocation: captured CUDA graphs hold raw pointers
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   int ensure(size_t need) {
     if (need <= bytes) return 0;
+    ++g_alloc_gen;
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
@@ -172,6 +175,17 @@ struct S7bEngine {
   cudaStream_t side[kMaxL] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxL] = {nullptr, nullptr, nullptr, nullptr};
   bool concurrent = true;
+  // Per-edge buffers are strided / gridded by a capacity E_cap >= n_edges and the edge kernels read the
+  // live edge count from d_nE, so that one captured CUDA graph of the whole step can be replayed while
+  // the neighbour count drifts between MD steps.
+  int64_t E_cap = 0;
+  DevBuf d_nE;
+  cudaGraphExec_t gexec = nullptr;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t g_in = nullptr, g_out = nullptr;
+  std::vector<int64_t> g_key;
+  int64_t g_launches_per_replay = 0;
+  int64_t g_captures = 0, g_replays = 0;
 };
 
 struct S7bConvPlan {
@@ -286,6 +300,7 @@ static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* 
 
 static int g_opt_atomic_virial = 0;   // engines created afterwards also produce the per-atom virial
 static int g_opt_concurrent = 1;   // co-schedule the per-l1 convolution kernels of a layer on side streams
+static int g_opt_cuda_graph = 1;   // s7b_engine_compute replays a captured CUDA graph of the step (table mode)
 static int g_opt_tc_gemm = 0;   // 1: node linears on tcgen05 (3xTF32); default FP32 SIMT
 
 // hi = rna_tf32(w), lo = rna_tf32(w - hi)   (see tc_gemm.cuh)
@@ -297,6 +312,8 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
     lo[i] = rna_tf32(v - h);
   }
 }
+
+__global__ void set_i64_kernel(int64_t* p, int64_t v) { *p = v; }
 
 // CSR over centres from a centre-sorted edge list, with validation (thread e handles the row starts
 // between centre[e-1] and centre[e]; thread n_edges closes the tail).  flag: 1 = not sorted / centre out
@@ -471,6 +488,7 @@ int s7b_set_option(const char* name, int value) {
   if (std::string(name) == "tc_gemm") { g_opt_tc_gemm = value; return 0; }
   if (std::string(name) == "atomic_virial") { g_opt_atomic_virial = value; return 0; }
   if (std::string(name) == "concurrent_conv") { g_opt_concurrent = value; return 0; }
+  if (std::string(name) == "cuda_graph") { g_opt_cuda_graph = value; return 0; }
   return fail(std::string("unknown option: ") + name);
 }
 
@@ -565,6 +583,11 @@ void s7b_engine_destroy(S7bEngine* e) {
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->gexec) cudaGraphExecDestroy(e->gexec);
+  if (e->gstream) cudaStreamDestroy(e->gstream);
+  if (e->g_in) cudaEventDestroy(e->g_in);
+  if (e->g_out) cudaEventDestroy(e->g_out);
+  e->d_nE.release();
   for (auto& kv : e->params) kv.second.release();
   for (auto& L : e->layers)
     for (auto& kv : L.params) kv.second.release();
@@ -618,7 +641,6 @@ static const float* gparam(const S7bEngine* e, const char* name) {
 int s7b_engine_set_graph(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t n_edges,
                          const int32_t* d_species, const int32_t* d_rowptr, const int32_t* d_src,
                          const float* d_edge_vec, void* stream) {
-  (void)stream;
   if (!e) return fail("null engine");
   if (n_local < 0 || n_nodes < n_local || n_edges < 0) return fail("bad graph sizes");
   if (n_edges >= ((int64_t)1 << 31)) return fail("more than 2^31-1 edges per GPU are not supported");
@@ -630,7 +652,12 @@ int s7b_engine_set_graph(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t
   e->d_src = d_src;
   e->d_edge_vec = d_edge_vec;
   const bool table = e->desc.table_knots > 0;
-  const size_t E = (size_t)std::max<int64_t>(n_edges, 1), Nn = (size_t)std::max(n_nodes, 1), Nl = (size_t)std::max(n_local, 1);
+  if (n_edges > e->E_cap || 2 * n_edges < e->E_cap)   // a little headroom, so MD-step fluctuations keep the capacity
+    e->E_cap = (n_edges + n_edges / 32 + 1024) / 1024 * 1024;
+  if (e->d_nE.ensure(sizeof(int64_t))) return fail("cudaMalloc failed");
+  set_i64_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(e->d_nE.as<int64_t>(), n_edges);
+  S7B_LAUNCH_CHECK();
+  const size_t E = (size_t)e->E_cap, Nn = (size_t)std::max(n_nodes, 1), Nl = (size_t)std::max(n_local, 1);
   const int T = e->desc.n_layers;
   int rc = 0;
   rc |= e->rec.ensure(E * sizeof(int4));
@@ -720,6 +747,8 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
   const int T = e->desc.n_layers;
   const int Nn = e->n_nodes, Nl = e->n_local;
   const int64_t E = e->n_edges;
+  const int64_t Ecap = e->E_cap;          // stride of the per-l1 parts of dY_acc / dEdr_acc, grid of the edge kernels
+  const int64_t* nE = e->d_nE.as<int64_t>();
   const bool table = e->desc.table_knots > 0;
   const int LF = e->desc.lmax_filter;
   if (!e->radial_ready) return fail("parameter 'bessel' was not set");
@@ -728,17 +757,17 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
     case S7B_STAGE_FWD_BEGIN: {
       if (E > 0) {
         const int blk = 256;
-        const int grd = (int)((E + blk - 1) / blk);
+        const int grd = (int)((Ecap + blk - 1) / blk);
         float* emb = table ? nullptr : e->emb.as<float>();
         ProfScope ps(e->prof, st, "edge_fwd");
-        if (LF == 1) edge_fwd_kernel<1><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
-        else if (LF == 2) edge_fwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
-        else edge_fwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, E, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
+        if (LF == 1) edge_fwd_kernel<1><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, nE, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
+        else if (LF == 2) edge_fwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, nE, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
+        else edge_fwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, e->d_src, nE, e->ny_stride, e->rec.as<int4>(), e->Y.as<float>(), e->rlen.as<float>(), emb);
         S7B_LAUNCH_CHECK();
         int max_lx = 0;
         for (auto& L : e->layers) max_lx = std::max(max_lx, L.n_lx);
-        S7B_CUDA_CHECK(cudaMemsetAsync(e->dY_acc.p, 0, (size_t)max_lx * E * e->ny_stride * sizeof(float), st));
-        S7B_CUDA_CHECK(cudaMemsetAsync(e->dEdr_acc.p, 0, (size_t)max_lx * E * sizeof(float), st));
+        S7B_CUDA_CHECK(cudaMemsetAsync(e->dY_acc.p, 0, (size_t)max_lx * Ecap * e->ny_stride * sizeof(float), st));
+        S7B_CUDA_CHECK(cudaMemsetAsync(e->dEdr_acc.p, 0, (size_t)max_lx * Ecap * sizeof(float), st));
         if (!table) S7B_CUDA_CHECK(cudaMemsetAsync(e->demb_acc.p, 0, (size_t)E * e->desc.n_basis * sizeof(float), st));
       }
       const LayerCfg& L0 = e->layers[0];
@@ -862,8 +891,8 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         const bool par = e->concurrent && g_opt_concurrent && !e->prof.enabled && L.n_lx > 1;
         if (par) S7B_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
         for (int l1 = 0; l1 < L.n_lx; ++l1) {
-          float* dY = e->dY_acc.as<float>() + (size_t)l1 * E * e->ny_stride;
-          float* dEdr = e->dEdr_acc.as<float>() + (size_t)l1 * E;
+          float* dY = e->dY_acc.as<float>() + (size_t)l1 * Ecap * e->ny_stride;
+          float* dEdr = e->dEdr_acc.as<float>() + (size_t)l1 * Ecap;
           cudaStream_t s1 = (par && l1 > 0) ? e->side[l1] : st;
           if (par && l1 > 0) S7B_CUDA_CHECK(cudaStreamWaitEvent(s1, e->ev_fork, 0));
           ProfScope ps(e->prof, s1, "conv_bwd", t, l1);
@@ -914,15 +943,15 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       if (av) S7B_CUDA_CHECK(cudaMemsetAsync(e->atomic_virial.p, 0, (size_t)std::max(Nn, 1) * 6 * sizeof(float), st));
       if (E > 0 && Nl > 0) {
         const int blk = 256;
-        const int grd = (int)((E + blk - 1) / blk);
+        const int grd = (int)((Ecap + blk - 1) / blk);
         int max_lx = 0;
         for (auto& L : e->layers) max_lx = std::max(max_lx, L.n_lx);
         const float* dEdr = table ? e->dEdr_acc.as<float>() : nullptr;
         const float* demb = table ? nullptr : e->demb_acc.as<float>();
         ProfScope ps(e->prof, st, "edge_bwd_force_scatter");
-        if (LF == 1) edge_bwd_kernel<1><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
-        else if (LF == 2) edge_bwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
-        else edge_bwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, E, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
+        if (LF == 1) edge_bwd_kernel<1><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, nE, Ecap, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
+        else if (LF == 2) edge_bwd_kernel<2><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, nE, Ecap, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
+        else edge_bwd_kernel<3><<<grd, blk, 0, st>>>(e->radial, e->d_edge_vec, nE, Ecap, e->ny_stride, max_lx, e->dY_acc.as<float>(), dEdr, demb, e->fedge.as<float>());
         S7B_LAUNCH_CHECK();
         force_scatter_kernel<<<(Nl * 32 + blk - 1) / blk, blk, 0, st>>>(e->d_rowptr, e->d_src, e->d_edge_vec, e->fedge.as<float>(), Nl, e->forces.as<float>(), e->virial.as<double>(), av ? e->atomic_virial.as<float>() : nullptr);
         S7B_LAUNCH_CHECK();
@@ -934,8 +963,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
   }
 }
 
-int s7b_engine_compute(S7bEngine* e, void* stream) {
-  if (!e) return fail("null engine");
+static int run_all_stages(S7bEngine* e, void* stream) {
   const int T = e->desc.n_layers;
   if (s7b_engine_run_stage(e, S7B_STAGE_FWD_BEGIN, 0, stream)) return 1;
   for (int t = 0; t < T; ++t)
@@ -946,6 +974,62 @@ int s7b_engine_compute(S7bEngine* e, void* stream) {
     if (t > 0 && s7b_engine_run_stage(e, S7B_STAGE_BWD_LAYER_B, t, stream)) return 1;
   }
   return s7b_engine_run_stage(e, S7B_STAGE_BWD_END, 0, stream);
+}
+
+// The whole step is ~75 launches; below a few thousand atoms their launch latency, not the kernels, sets
+// the step time.  The step is therefore captured once into a CUDA graph (on an engine-owned stream,
+// side-stream fork/joins included) and replayed for as long as nothing baked into it changes: sizes,
+// edge capacity, graph-array pointers, any (re)allocation, the options.  The live edge count is read
+// from device memory by the edge kernels (see S7bEngine::E_cap), so MD steps with a drifting
+// neighbour count replay the same graph.
+int s7b_engine_compute(S7bEngine* e, void* stream) {
+  if (!e) return fail("null engine");
+  const bool table = e->desc.table_knots > 0;
+  if (!g_opt_cuda_graph || !table || e->prof.enabled) return run_all_stages(e, stream);
+  if (!e->radial_ready) return fail("parameter 'bessel' was not set");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!e->gstream) {
+    S7B_CUDA_CHECK(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
+    S7B_CUDA_CHECK(cudaEventCreateWithFlags(&e->g_in, cudaEventDisableTiming));
+    S7B_CUDA_CHECK(cudaEventCreateWithFlags(&e->g_out, cudaEventDisableTiming));
+  }
+  const std::vector<int64_t> key = {
+      e->n_nodes, e->n_local, e->E_cap, e->n_edges > 0 ? 1 : 0, (int64_t)(uintptr_t)e->d_species,
+      (int64_t)(uintptr_t)e->d_rowptr, (int64_t)(uintptr_t)e->d_src, (int64_t)(uintptr_t)e->d_edge_vec,
+      g_alloc_gen, g_opt_concurrent, g_opt_tc_gemm, e->concurrent ? 1 : 0};
+  if (!e->gexec || key != e->g_key) {
+    if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
+    const int64_t before = g_launches + g_conv_launches;
+    S7B_CUDA_CHECK(cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_all_stages(e, e->gstream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
+    const int64_t captured = g_launches + g_conv_launches - before;
+    g_launches -= captured;                 // recorded, not launched
+    if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+    if (ce != cudaSuccess) { cudaGetLastError(); return fail(std::string("CUDA graph capture failed: ") + cudaGetErrorString(ce)); }
+    const cudaError_t ci = cudaGraphInstantiate(&e->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ci != cudaSuccess) { e->gexec = nullptr; cudaGetLastError(); return fail(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ci)); }
+    e->g_key = key;
+    e->g_launches_per_replay = captured;
+    ++e->g_captures;
+  }
+  S7B_CUDA_CHECK(cudaEventRecord(e->g_in, st));
+  S7B_CUDA_CHECK(cudaStreamWaitEvent(e->gstream, e->g_in, 0));
+  S7B_CUDA_CHECK(cudaGraphLaunch(e->gexec, e->gstream));
+  S7B_CUDA_CHECK(cudaEventRecord(e->g_out, e->gstream));
+  S7B_CUDA_CHECK(cudaStreamWaitEvent(st, e->g_out, 0));
+  g_launches += e->g_launches_per_replay;
+  ++e->g_replays;
+  return 0;
+}
+
+int s7b_engine_graph_stats(S7bEngine* e, int64_t* captures, int64_t* replays) {
+  if (!e) return fail("null engine");
+  if (captures) *captures = e->g_captures;
+  if (replays) *replays = e->g_replays;
+  return 0;
 }
 
 int s7b_engine_set_profiling(S7bEngine* e, int enable) {

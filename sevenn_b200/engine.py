@@ -49,7 +49,7 @@ EXPORTS = [
     's7b_last_error', 's7b_version', 's7b_set_option', 's7b_dense_linear', 's7b_engine_create', 's7b_engine_destroy',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
     's7b_engine_buffer', 's7b_engine_compute_host', 's7b_engine_set_positions_host',
-    's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_set_profiling',
+    's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_graph_stats', 's7b_engine_set_profiling',
     's7b_engine_profile_count', 's7b_engine_profile_entry', 's7b_conv_plan_create',
     's7b_conv_plan_destroy', 's7b_conv_plan_dims', 's7b_conv_forward', 's7b_conv_backward',
 ]
@@ -87,6 +87,7 @@ def load_library() -> ctypes.CDLL:
                                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.s7b_launch_count.argtypes = [ctypes.c_int]
     lib.s7b_launch_count.restype = i64
+    lib.s7b_engine_graph_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.s7b_conv_plan_create.argtypes = [i32, ctypes.POINTER(i32), i32, i32, ctypes.POINTER(vp)]
     lib.s7b_conv_plan_destroy.argtypes = [vp]
     lib.s7b_conv_plan_destroy.restype = None
@@ -459,6 +460,12 @@ class B200Engine:
             check(self.lib.s7b_engine_profile_entry(self._h, i, name, 96, ctypes.byref(ms), ctypes.byref(calls)))
             out[name.value.decode()] = (ms.value, calls.value)
         return out
+
+    def graph_stats(self):
+        """(captures, replays) of the CUDA-graph path of ``compute``."""
+        c, r = ctypes.c_int64(), ctypes.c_int64()
+        check(self.lib.s7b_engine_graph_stats(self._h, ctypes.byref(c), ctypes.byref(r)))
+        return int(c.value), int(r.value)
 
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.s7b_launch_count(1 if reset else 0))

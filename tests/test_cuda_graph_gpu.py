@@ -1,0 +1,87 @@
+"""CUDA-graph replay of the step (s7b_engine_compute): identical results to direct launches, replay
+across MD steps whose neighbour count changes, recapture when sizes change."""
+import numpy as np
+import pytest
+
+from helpers import model_weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def engine():
+    from sevenn_b200.engine import B200Engine, set_option
+    meta, arrays = model_weights('sevennet_0')
+    set_option('cuda_graph', 1)
+    yield B200Engine(meta, arrays)
+    set_option('cuda_graph', 1)
+
+
+def _si(reps, seed=0, sigma=0.05):
+    from sevenn_b200.neighbors import diamond_si
+    pos, cell, _ = diamond_si(*reps, sigma=sigma, seed=seed)
+    return pos, cell
+
+
+def test_replay_equals_direct_launches(engine):
+    import torch
+    from sevenn_b200.engine import set_option
+    pos, cell = _si((2, 2, 2))
+    sp = np.full(len(pos), engine.spec.type_map[14], dtype=np.int32)
+    engine.set_positions(sp, pos, cell, True)
+    set_option('cuda_graph', 0)
+    engine.compute(); torch.cuda.synchronize()
+    ref = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
+    assert engine.graph_stats() == (0, 0)
+    set_option('cuda_graph', 1)
+    engine.launch_count(reset=True)
+    for _ in range(4):
+        engine.compute()
+    torch.cuda.synchronize()
+    n_launch = engine.launch_count()
+    out = {k: v.cpu().numpy() for k, v in engine.results().items()}
+    assert engine.graph_stats() == (1, 4)
+    assert n_launch % 4 == 0 and n_launch // 4 > 40          # replays are counted, the capture itself is not
+    assert abs(out['energy'][0] - ref['energy'][0]) < 1e-6
+    assert np.allclose(out['atomic_energy'], ref['atomic_energy'], atol=1e-6)
+    assert np.allclose(out['forces'], ref['forces'], atol=2e-6)       # RED.ADD order differs between runs
+    assert np.allclose(out['virial'], ref['virial'], atol=1e-5)
+
+
+def test_replay_across_md_steps_with_changing_neighbour_count(engine):
+    from sevenn_b200.engine import set_option
+    pos, cell = _si((3, 3, 3))
+    sp = np.full(len(pos), engine.spec.type_map[14], dtype=np.int32)
+    rng = np.random.RandomState(1)
+    counts = []
+    for step in range(8):
+        pos = pos + rng.normal(scale=0.02, size=pos.shape)
+        set_option('cuda_graph', 1)
+        e1, ae1, f1, v1, n1 = engine.compute_positions(sp, pos, cell, True)
+        set_option('cuda_graph', 0)
+        e0, ae0, f0, v0, n0 = engine.compute_positions(sp, pos, cell, True)
+        assert n0 == n1
+        counts.append(n1)
+        assert abs(e1 - e0) < 1e-6 and np.allclose(f1, f0, atol=2e-6) and np.allclose(v1, v0, atol=1e-5)
+    set_option('cuda_graph', 1)
+    assert len(set(counts)) > 1, counts            # the neighbour count did change ...
+    captures, replays = engine.graph_stats()
+    assert replays == 8 and captures <= 2, (captures, replays, counts)   # ... and the captured step was reused
+
+
+def test_recapture_when_the_system_changes(engine):
+    from oracle.oracle import Oracle   # noqa: F401  (oracle import path check only)
+    import torch
+    res = {}
+    for reps in [(2, 2, 2), (4, 4, 4), (2, 2, 2), (1, 1, 1)]:
+        pos, cell = _si(reps)
+        sp = np.full(len(pos), engine.spec.type_map[14], dtype=np.int32)
+        e, ae, f, v, n = engine.compute_positions(sp, pos, cell, True)
+        torch.cuda.synchronize()
+        if reps in res:
+            assert abs(res[reps][0] - e) < 1e-6 and np.allclose(res[reps][1], f, atol=2e-6)
+        res[reps] = (e, f)
+        assert np.isfinite(e) and abs(e / len(pos) + 5.3655) < 0.05      # Si: -5.3655 eV/atom for this jitter
+    # an empty neighbour list (isolated atom) also goes through the graph path
+    e, ae, f, v, n = engine.compute_positions(sp[:1], np.zeros((1, 3)), np.eye(3) * 20.0, True)
+    assert n == 0 and np.allclose(f, 0.0) and np.isfinite(e)
