@@ -26,9 +26,47 @@
 namespace s7b {
 
 constexpr int kConvWarpsPerBlock = 4;
-#ifndef S7B_PREFETCH
-#define S7B_PREFETCH 0   // measured: prefetching the next edge record costs registers and is slower (r1)
+// Register budget, as the min-resident-CTAs argument of __launch_bounds__ (128-thread CTAs: 4 -> 128
+// registers, 3 -> 168, 1 -> 255).  Measured on B200 (7net-0, 12k atoms, A/B inside one box):
+//  * forward: an explicit 1 lets ptxas keep more gathers in flight for the l1 = 0 kernels (96 -> 128
+//    registers, -22 % time); the l1 >= 1 kernels do not change;
+//  * backward: l1 = 0 is fastest at 3 (-6 %), l1 = 1 at 4 (128 registers; 168 or 220 are 3-4 % slower),
+//    l1 >= 2 at 3 (what ptxas picks by itself).  The lmax = 3 kinds need > 168 registers (they spill
+//    otherwise) and are left at 2.
+#ifndef S7B_FWD_MINBLOCKS
+#define S7B_FWD_MINBLOCKS 1
 #endif
+#define S7B_FWD_BOUNDS __launch_bounds__(32 * kConvWarpsPerBlock, S7B_FWD_MINBLOCKS)
+#ifdef S7B_BWD_MINBLOCKS
+#define S7B_BWD_BOUNDS __launch_bounds__(32 * kConvWarpsPerBlock, S7B_BWD_MINBLOCKS)
+#else
+#define S7B_BWD_BOUNDS __launch_bounds__(32 * kConvWarpsPerBlock, (Kind::NY != 9) ? 2 : ((Kind::D1 == 3) ? 4 : 3))
+#endif
+#ifndef S7B_COOP_REC
+#define S7B_COOP_REC 1   // lanes of a group fetch the records of LPN consecutive edges at once (see EdgeRecs)
+#endif
+
+// The 16-byte edge record {neighbour, table interval, frac} heads the per-edge dependency chain
+// (record -> gather address / table address -> loads -> math).  Loading it per edge costs one
+// dependent L2 round trip per edge; instead lane i of a group loads the record of edge e0 + i of the
+// row (one coalesced 16*LPN-byte request per LPN edges, i.e. about once per row) and every iteration
+// takes its record by shuffle.  Prefetching record + harmonics into registers was measured slower
+// (register pressure); this costs three registers.
+template <int LPN>
+struct EdgeRecs {
+  int cx, cy, cz;
+  __device__ __forceinline__ void fill(const ConvArgs& a, int e0, int len, int it, int sl) {
+    const int ei = it + sl;
+    int4 r = make_int4(0, 0, 0, 0);
+    if (ei < len) r = __ldg(a.rec + e0 + ei);
+    cx = r.x; cy = r.y; cz = r.z;
+  }
+  __device__ __forceinline__ int4 get(int it) const {
+    const int l = it % LPN;
+    return make_int4(__shfl_sync(0xffffffffu, cx, l, LPN), __shfl_sync(0xffffffffu, cy, l, LPN),
+                     __shfl_sync(0xffffffffu, cz, l, LPN), 0);
+  }
+};
 
 // Sum M values (M = 8 or 16) over the LPN lanes of a group with ~M-1+log2(LPN/M) shuffles instead
 // of M*log2(LPN).  On return v[0] of group-lane sl holds the total of value (sl / (LPN/M)) % M.
@@ -141,7 +179,7 @@ struct LaneMap {
 // grid = (ceil(n_dst / (kConvWarpsPerBlock * 32/LPN)), mul / (2*LPN*NV)), block = 32*kConvWarpsPerBlock
 // ------------------------------------------------------------------------------------------
 template <class Kind, int NV, int LPN, bool TABLE, class V>
-__global__ void __launch_bounds__(32 * kConvWarpsPerBlock)
+__global__ void S7B_FWD_BOUNDS
 conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) {
   constexpr int CH = VT<V>::CH;
   const LaneMap<NV, LPN, CH> m(a);
@@ -153,35 +191,18 @@ conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) 
 #pragma unroll
     for (int q = 0; q < Kind::NACC; ++q) acc[c][q] = VT<V>::zero();
 
-  // software pipeline: the edge record and harmonics of iteration it+1 are requested before the
-  // gathers of iteration it, taking one dependent L2 round trip off the per-edge critical path
-  int4 rec_n = make_int4(0, 0, 0, 0);
-  float Y_n[Kind::NY];
-  if (m.nmax > 0) {
-    const int e = (m.len > 0) ? m.e0 : 0;
-    rec_n = __ldg(a.rec + e);
-    load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y_n);
-  }
+  EdgeRecs<LPN> recs;
   for (int it = 0; it < m.nmax; ++it) {
     const bool valid = (LPN == 32) || (it < m.len);
     const int e = valid ? m.e0 + it : 0;
-#if S7B_PREFETCH
-    const int4 rec = rec_n;
-    float Y[Kind::NY];
-#pragma unroll
-    for (int j = 0; j < Kind::NY; ++j) Y[j] = Y_n[j];
+#if S7B_COOP_REC
+    if (it % LPN == 0) recs.fill(a, m.e0, m.len, it, m.sl);
+    const int4 rec = recs.get(it);
 #else
     const int4 rec = __ldg(a.rec + e);
+#endif
     float Y[Kind::NY];
     load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y);
-#endif
-#if S7B_PREFETCH
-    if (it + 1 < m.nmax) {
-      const int en = (it + 1 < m.len) ? m.e0 + it + 1 : 0;
-      rec_n = __ldg(a.rec + en);
-      load_Y<Kind>(a.Y + (size_t)en * a.ny_stride, Y_n);
-    }
-#endif
     const float* __restrict__ xrow = a.x + (size_t)rec.x * a.dim_x + role.x_off;
     const float tt = __int_as_float(rec.z);
 #pragma unroll
@@ -228,7 +249,7 @@ conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) 
 // dY_acc / dEdr_acc / dw rows are owned by exactly one group of one launch: plain read-modify-write.
 // ------------------------------------------------------------------------------------------
 template <class Kind, int NV, int LPN, bool TABLE, bool NEED_DX, bool SPLIT>
-__global__ void __launch_bounds__(32 * kConvWarpsPerBlock)
+__global__ void S7B_BWD_BOUNDS
 conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__ gout,
                 float* __restrict__ dx, float* __restrict__ dY_acc, float* __restrict__ dEdr_acc,
                 float* __restrict__ dw) {
@@ -250,33 +271,23 @@ conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__
   }
 
   constexpr int NR = (Kind::NY <= 9) ? 8 : 16;   // values reduced with the transposing butterfly
-  int4 rec_n;
-  float Y_n[Kind::NY];
-  {
-    const int e = (m.len > 0) ? m.e0 : 0;
-    rec_n = __ldg(a.rec + e);
-    load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y_n);
-  }
+  constexpr bool RIDE = TABLE && (Kind::NY - 1 < NR);     // a free slot of the butterfly carries dE/dr
+  constexpr int PER = LPN / NR;
+  const int idx = (m.sl / PER) % NR;                      // which reduced value ends up in this lane
+  const bool is_dY = idx + 1 < Kind::NY;
+  const bool writer = (m.sl % PER) == 0 && (is_dY || (RIDE && idx == NR - 1));
+  EdgeRecs<LPN> recs;
   for (int it = 0; it < m.nmax; ++it) {
     const bool valid = (LPN == 32) || (it < m.len);
     const int e = valid ? m.e0 + it : 0;
-#if S7B_PREFETCH
-    const int4 rec = rec_n;
-    float Y[Kind::NY];
-#pragma unroll
-    for (int j = 0; j < Kind::NY; ++j) Y[j] = Y_n[j];
+#if S7B_COOP_REC
+    if (it % LPN == 0) recs.fill(a, m.e0, m.len, it, m.sl);
+    const int4 rec = recs.get(it);
 #else
     const int4 rec = __ldg(a.rec + e);
+#endif
     float Y[Kind::NY];
     load_Y<Kind>(a.Y + (size_t)e * a.ny_stride, Y);
-#endif
-#if S7B_PREFETCH
-    if (it + 1 < m.nmax) {
-      const int en = (it + 1 < m.len) ? m.e0 + it + 1 : 0;
-      rec_n = __ldg(a.rec + en);
-      load_Y<Kind>(a.Y + (size_t)en * a.ny_stride, Y_n);
-    }
-#endif
     const float* __restrict__ xrow = a.x + (size_t)rec.x * a.dim_x + role.x_off;
     const float tt = __int_as_float(rec.z);
     V2 dY[Kind::NY];
@@ -321,24 +332,17 @@ conv_bwd_kernel(const ConvArgs a, const ConvRole role, const float* __restrict__
     }
     // cross-channel reduction of dE/dY (NY-1 values) and dE/dr (1 value) over the group
     const float dEdr = dEdr2.x + dEdr2.y;
-    constexpr bool RIDE = TABLE && (Kind::NY - 1 < NR);     // a free slot carries dE/dr
     float red[NR];
 #pragma unroll
     for (int j = 0; j < NR; ++j) red[j] = (j + 1 < Kind::NY) ? dY[j + 1].x + dY[j + 1].y : 0.0f;
     if (RIDE) red[NR - 1] = dEdr;
     group_reduce_multi<NR, LPN>(red, m.sl);
-    constexpr int PER = LPN / NR;
-    const int idx = (m.sl / PER) % NR;
     // a (node, l1) role normally belongs to one group -> plain read-modify-write (deterministic);
     // SPLIT (launched with gridDim.y > 1: the role's channels are spread over several CTAs) adds atomically
-    if (valid && (m.sl % PER) == 0) {
-      if (idx + 1 < Kind::NY) {
-        if (SPLIT) atomicAdd(dY_acc + (size_t)e * a.ny_stride + idx, red[0]);
-        else dY_acc[(size_t)e * a.ny_stride + idx] += red[0];
-      } else if (RIDE && idx == NR - 1) {
-        if (SPLIT) atomicAdd(dEdr_acc + e, red[0]);
-        else dEdr_acc[e] += red[0];
-      }
+    if (valid && writer) {
+      float* dst = is_dY ? dY_acc + (size_t)e * a.ny_stride + idx : dEdr_acc + e;
+      if (SPLIT) atomicAdd(dst, red[0]);
+      else *dst += red[0];      // (requesting the old value at the top of the iteration was measured 1 % slower)
     }
     if (TABLE && !RIDE) {
       const float s = group_sum<LPN>(dEdr);

@@ -17,9 +17,9 @@ def engine():
     set_option('cuda_graph', 1)
 
 
-def _si(reps, seed=0, sigma=0.05):
+def _si(reps, seed=0, sigma=0.05, a=5.431):
     from sevenn_b200.neighbors import diamond_si
-    pos, cell, _ = diamond_si(*reps, sigma=sigma, seed=seed)
+    pos, cell, _ = diamond_si(*reps, a=a, sigma=sigma, seed=seed)
     return pos, cell
 
 
@@ -50,7 +50,7 @@ def test_replay_equals_direct_launches(engine):
 
 def test_replay_across_md_steps_with_changing_neighbour_count(engine):
     from sevenn_b200.engine import set_option
-    pos, cell = _si((3, 3, 3))
+    pos, cell = _si((3, 3, 3), a=6.03)      # stretched: the sqrt(11)/4 a shell sits at the 5 A cutoff
     sp = np.full(len(pos), engine.spec.type_map[14], dtype=np.int32)
     rng = np.random.RandomState(1)
     counts = []

@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sevenn_b200.checkpoint import load_weights  # noqa: E402
-from sevenn_b200.engine import B200Engine  # noqa: E402
+from sevenn_b200.engine import B200Engine, set_option  # noqa: E402
 from sevenn_b200.neighbors import diamond_si  # noqa: E402
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -19,6 +19,7 @@ def main():
     model = sys.argv[1] if len(sys.argv) > 1 else 'sevennet_0'
     max_atoms = int(sys.argv[2]) if len(sys.argv) > 2 else 1_100_000
     meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{model}.npz'))
+    set_option('cuda_graph', int(os.environ.get('S7B_CUDA_GRAPH', '1')))
     eng = B200Engine(meta, arrays)
     si = eng.spec.type_map[14]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
@@ -44,7 +45,7 @@ def main():
             ms.append(a.elapsed_time(b))
         med = float(np.median(ms))
         row = dict(atoms=n, edges=eng.n_edges, ms_per_step=round(med, 4), atom_updates_per_s=round(n / med * 1e3),
-                   nl_ms_incl_h2d=round(nl_ms, 3), mem_gb=round(torch.cuda.max_memory_allocated() / 2**30, 2),
+                   nl_ms_incl_h2d=round(nl_ms, 3), mem_gb=round((torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 2**30, 2),
                    energy_per_atom=float(eng.buffer('energy', dtype='f8')[0]) / n)
         print(json.dumps(row), flush=True)
         rows.append(row)
