@@ -382,8 +382,14 @@ def roofline_from_profile(eng, prof, n_edges, n_dst):
         out['l2_gbs'] = (hbm + l2) / (ms * 1e-3) / 1e9
         out['fp32'] = {'achieved_tflops': flops / (ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
                        'frac': flops / (ms * 1e-3) / 1e12 / fp32_peak}
+        try:   # dram bytes per launch of this kernel kind from the committed ncu --set full capture (mid layers, 12k atoms)
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+            if 1 <= t <= 3 and n_dst == 12000:
+                out['traffic'] = tr.get('sevennet_0' if eng.spec.lmax_filter == 2 else 'none', {}).get(f'{parts[0]}.l{l1}')
+        except Exception:
+            pass
         out['note'] = ('not HBM-bound: x and the radial tables are L2-resident; ncu (profiles/) shows the FP32 '
-                       'pipe and L1/L2 latency as the limiters; traffic = ncu dram bytes, see profiles/')
+                       'pipe and L1/L2 latency as the limiters; traffic = ncu dram bytes per launch from profiles/ncu_traffic.json')
     return out, breakdown
 
 
