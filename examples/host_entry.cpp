@@ -15,7 +15,7 @@
 #include <string>
 #include <vector>
 
-#include "../include/sevenn_b200.h"
+#include "s7b_model_file.h"
 
 #define CHECK(call)                                                     \
   do {                                                                  \
@@ -25,7 +25,7 @@
     }                                                                   \
   } while (0)
 
-static bool read_exact(FILE* f, void* p, size_t n) { return std::fread(p, 1, n, f) == n; }
+using s7b_file::read_exact;
 
 int main(int argc, char** argv) {
   if (argc < 3) {
@@ -33,38 +33,17 @@ int main(int argc, char** argv) {
     return 2;
   }
   // ---- model -------------------------------------------------------------------------------------
-  FILE* f = std::fopen(argv[1], "rb");
-  if (!f) { std::perror(argv[1]); return 2; }
-  char magic[8];
-  int32_t version = 0, n_arrays = 0, n_types = 0;
-  S7bModelDesc desc;
-  if (!read_exact(f, magic, 8) || std::memcmp(magic, "S7BMODEL", 8) != 0 || !read_exact(f, &version, 4) ||
-      version != 1 || !read_exact(f, &desc, sizeof(desc)) || !read_exact(f, &n_arrays, 4) || !read_exact(f, &n_types, 4)) {
-    std::fprintf(stderr, "bad model file\n");
+  s7b_file::Model model;
+  const std::string err = s7b_file::load(argv[1], model);
+  if (!err.empty()) {
+    std::fprintf(stderr, "%s\n", err.c_str());
     return 2;
   }
-  std::map<int, int> type_map;
-  for (int i = 0; i < n_types; ++i) {
-    int32_t zi[2];
-    if (!read_exact(f, zi, 8)) return 2;
-    type_map[zi[0]] = zi[1];
-  }
-  S7bEngine* eng = nullptr;
-  CHECK(s7b_engine_create(&desc, &eng));
-  std::vector<float> buf;
-  for (int a = 0; a < n_arrays; ++a) {
-    char name[33] = {0};
-    int32_t layer = 0;
-    int64_t numel = 0;
-    if (!read_exact(f, name, 32) || !read_exact(f, &layer, 4) || !read_exact(f, &numel, 8)) return 2;
-    buf.resize((size_t)numel);
-    if (!read_exact(f, buf.data(), (size_t)numel * sizeof(float))) return 2;
-    CHECK(s7b_engine_set_param(eng, name, layer, buf.data(), (size_t)numel));
-  }
-  std::fclose(f);
+  S7bEngine* eng = model.engine;
+  const std::map<int, int>& type_map = model.species_of_z;
 
   // ---- input -------------------------------------------------------------------------------------
-  f = std::fopen(argv[2], "rb");
+  FILE* f = std::fopen(argv[2], "rb");
   if (!f) { std::perror(argv[2]); return 2; }
   int32_t n = 0;
   double energy = 0.0, virial[6];

@@ -1,0 +1,65 @@
+// Minimal stand-ins for the LAMMPS declarations examples/lammps/pair_e3gnn_b200.cpp uses, only so that
+// the pair style can be syntax-checked without LAMMPS (g++ -fsyntax-only).  Not LAMMPS code: member
+// names and signatures follow the public LAMMPS developer documentation (stable_2Aug2023).
+#pragma once
+#include <cstdint>
+#define FLERR __FILE__, __LINE__
+#define NEIGHMASK 0x1FFFFFFF
+namespace LAMMPS_NS {
+typedef int tagint;
+class LAMMPS;
+struct Error {
+  [[noreturn]] void all(const char *, int, const char *);
+  [[noreturn]] void one(const char *, int, const char *);
+};
+struct Memory {
+  template <class T> T **create(T **&a, int, int, const char *) { return a; }
+  template <class T> T *create(T *&a, int, const char *) { return a; }
+  template <class T> void destroy(T &) {}
+};
+struct Atom {
+  enum { MAP_NONE = 0, MAP_ARRAY = 1, MAP_HASH = 2, MAP_YES = 3 };
+  int ntypes, nlocal, nghost, map_style;
+  double **x, **f;
+  int *type;
+  tagint *tag;
+  int map(tagint);
+  int tag_consecutive();
+};
+struct Force { int newton_pair; };
+struct NeighList {
+  int inum;
+  int *ilist, *numneigh, **firstneigh;
+};
+namespace NeighConst { enum { REQ_DEFAULT = 0, REQ_FULL = 1 }; }
+struct Neighbor { void *add_request(class Pair *, int); };
+class Pointers {
+ public:
+  explicit Pointers(LAMMPS *) {}
+  virtual ~Pointers() = default;
+ protected:
+  Error *error;
+  Memory *memory;
+  Atom *atom;
+  Force *force;
+  Neighbor *neighbor;
+};
+class Pair : protected Pointers {
+ public:
+  explicit Pair(LAMMPS *lmp) : Pointers(lmp) {}
+  virtual void compute(int, int) = 0;
+  virtual void settings(int, char **) = 0;
+  virtual void coeff(int, char **) = 0;
+  virtual void init_style() {}
+  virtual double init_one(int, int) { return 0.0; }
+  double eng_vdwl, virial[6];
+  double *eatom, **vatom;
+ protected:
+  int allocated = 0, single_enable, restartinfo, one_coeff, manybody_flag, no_virial_fdotr_compute;
+  int eflag_global, eflag_atom, vflag_global, vflag_atom;
+  int **setflag;
+  double **cutsq;
+  NeighList *list;
+  void ev_init(int, int, int = 1);
+};
+}  // namespace LAMMPS_NS

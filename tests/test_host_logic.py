@@ -125,3 +125,15 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(eng, '_LIB_PATH', '/nonexistent/libsevenn_b200.so')
     with pytest.raises(ImportError, match='no CPU or PyTorch fallback'):
         eng.load_library()
+
+
+def test_cpp_examples_compile(tmp_path):
+    """examples/host_entry.cpp links against the built library; the LAMMPS pair style (no LAMMPS in the
+    image) at least passes a syntax check against minimal stand-in declarations."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, 'sevenn_b200', 'lib')
+    subprocess.run(['g++', '-std=c++17', '-Wall', '-Werror', os.path.join(root, 'examples', 'host_entry.cpp'), '-o',
+                    str(tmp_path / 'host_entry'), f'-L{lib_dir}', '-lsevenn_b200', f'-Wl,-rpath,{lib_dir}'], check=True)
+    subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-Werror', '-I', os.path.join(root, 'tests', 'mock_lammps'),
+                    os.path.join(root, 'examples', 'lammps', 'pair_e3gnn_b200.cpp')], check=True)
