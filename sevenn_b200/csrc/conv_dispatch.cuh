@@ -8,6 +8,15 @@
                           // (node, l1) role over two CTAs, whose per-edge dY/dE/dr sums then need atomics)
 #endif
 
+#ifndef S7B_FWD_L0_NV
+#define S7B_FWD_L0_NV 2   // channel pairs per lane in the l1 = 0 forward kernels (1 was measured 4 % slower)
+#endif
+#ifndef S7B_FWD_ODD_PAIRS
+#define S7B_FWD_ODD_PAIRS 1   // mul = 32 forward kernels: 1 = channel pairs on half warps (two nodes per warp, FFMA2),
+                              // 0 = one channel per lane.  Pairs are 29 % faster since the edge records are fetched
+                              // cooperatively (0.099 vs 0.139 ms, 7net-0 l1 = 2); before that the scalar form won.
+#endif
+
 namespace s7b {
 
 template <int LPN>
@@ -24,8 +33,7 @@ static int launch_fwd_one(bool table, const ConvArgs& a, const ConvRole& role, f
   return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// one channel per lane, a full warp per node: used in the forward when mul is an odd multiple of 32
-// (measured faster than two nodes per warp with channel pairs: r1, l1 = 2 kernels)
+// one channel per lane, a full warp per node (alternative forward mapping for mul = 32, see S7B_FWD_ODD_PAIRS)
 template <class Kind>
 static int launch_fwd_scalar(bool table, const ConvArgs& a, const ConvRole& role, float* out, cudaStream_t st) {
   dim3 grid((a.n_dst + kConvWarpsPerBlock - 1) / kConvWarpsPerBlock, role.mul / 32);
@@ -63,7 +71,11 @@ template <class Kind, int MAXNV>
 static int fwd_kind(bool table, const ConvArgs& a, const ConvRole& role, float* out, cudaStream_t st) {
   if (MAXNV >= 2 && role.mul % 128 == 0) return launch_fwd_one<Kind, MAXNV, 32>(table, a, role, out, st);
   if (role.mul % 64 == 0) return launch_fwd_one<Kind, 1, 32>(table, a, role, out, st);
+#if S7B_FWD_ODD_PAIRS
+  return launch_fwd_one<Kind, 1, 16>(table, a, role, out, st);
+#else
   return launch_fwd_scalar<Kind>(table, a, role, out, st);
+#endif
 }
 
 // ALLOW_NODX: only the l1 = 0 kinds are ever run without dx (first layer: x depends on species only)
@@ -85,7 +97,7 @@ static int bwd_kind(bool table, bool need_dx, const ConvArgs& a, const ConvRole&
   int launch_conv_fwd_##LF##_##LO(int l1, bool table, const ConvArgs& a, const ConvRole& role,     \
                                   float* out, cudaStream_t st) {                                   \
     switch (l1) {                                                                                  \
-      case 0: return fwd_kind<TPKind<0, LF, LO>, 2>(table, a, role, out, st);                      \
+      case 0: return fwd_kind<TPKind<0, LF, LO>, S7B_FWD_L0_NV>(table, a, role, out, st);                      \
       case 1: return fwd_kind<TPKind<1, LF, LO>, 1>(table, a, role, out, st);                      \
       case 2: return fwd_kind<TPKind<2, LF, LO>, 1>(table, a, role, out, st);                      \
       case 3: return fwd_kind<TPKind<(LF >= 3 ? 3 : 2), LF, LO>, 1>(table, a, role, out, st);      \
