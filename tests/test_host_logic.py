@@ -133,6 +133,9 @@ def test_cpp_examples_compile(tmp_path):
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     lib_dir = os.path.join(root, 'sevenn_b200', 'lib')
+    if not os.path.exists(os.path.join(lib_dir, 'libsevenn_b200.so')):
+        import __graft_entry__
+        __graft_entry__.build()
     subprocess.run(['g++', '-std=c++17', '-Wall', '-Werror', os.path.join(root, 'examples', 'host_entry.cpp'), '-o',
                     str(tmp_path / 'host_entry'), f'-L{lib_dir}', '-lsevenn_b200', f'-Wl,-rpath,{lib_dir}'], check=True)
     subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-Werror', '-I', os.path.join(root, 'tests', 'mock_lammps'),
