@@ -58,7 +58,7 @@ class FakeEngine:
     def buffer(self, name, t=0, dtype='f4', shape=None):
         return {'x': lambda: self.x[t], 'dx': lambda: self.dx, 'forces': lambda: self.forces,
                 'energy': lambda: self.energy, 'virial': lambda: self.virial,
-                'atomic_energy': lambda: torch.zeros(self.n_local)}[name]()
+                'atomic_energy': lambda: self.h.sum(1), 'edge_force': lambda: self.fedge}[name]()
 
     def run_stage(self, stage, t=0):
         nl = self.n_local
@@ -86,6 +86,7 @@ class FakeEngine:
             self.dh = self.coef[t - 1] * self.dx[:nl]
         elif stage == STAGE_BWD_END:
             f = self.dEdw[:, None] * self.vec / self.w[:, None]
+            self.fedge = f
             self.forces.zero_()
             self.forces.index_add_(0, self.dst, f)
             self.forces.index_add_(0, self.src, -f)
