@@ -161,6 +161,94 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def parity_tolerance(n_atoms):
+    """|dE| <= 1e-4 eV * sqrt(N/64), max|dF| <= 5e-5 eV/A."""
+    return 1e-4 * (max(n_atoms, 64) / 64.0) ** 0.5, 5e-5
+
+
+def oracle_parity(model, species, ei, ev, energy, forces, device):
+    """One-off comparison (outside every timed region) of the engine's result on the benchmark cell with
+    the fp64 oracle evaluated edge-chunked (oracle/oracle.py, `edge_chunk`) on `device`."""
+    import torch
+    from oracle.oracle import Oracle
+    from sevenn_b200.checkpoint import load_weights
+    meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{model}.npz'))
+    t0 = time.perf_counter()
+    o = Oracle(meta, arrays, dtype=torch.float64, device=device)
+    ref = o.forward(species, ei, ev, edge_chunk=32768)
+    if device != 'cpu':
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dE = float(energy) - float(ref['energy'])
+    dF = float(np.abs(np.asarray(forces, dtype=np.float64) - ref['forces'].cpu().numpy()).max())
+    tolE, tolF = parity_tolerance(len(species))
+    del o, ref
+    if device != 'cpu':
+        torch.cuda.empty_cache()
+    return {'against': f'oracle fp64 (torch on {device}, edge-chunked), same cell', 'dE_eV': dE, 'max_dF_eV_per_A': dF,
+            'dE_per_atom_eV': dE / len(species), 'tol_dE_eV': tolE, 'tol_dF_eV_per_A': tolF,
+            'ok': bool(abs(dE) <= tolE and dF <= tolF), 'oracle_seconds': dt}
+
+
+def gpu_standin(model, cells):
+    """torch-CUDA unfused stand-in of the reference GPU path (tools/gpu_standin.py), in a subprocess so
+    that its ~84 GiB of autograd state never coexists with the engine's buffers."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'gpu_standin.py'), model] + [str(c) for c in cells] + ['--json'],
+                           capture_output=True, text=True, timeout=600)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)
+        return {'error': (r.stderr or r.stdout)[-300:]}
+    except Exception as ex:   # noqa: BLE001
+        return {'error': repr(ex)[:300]}
+
+
+def time_steps(torch, step, steps, flush):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+
+def extra_model(args, model, cells, flush, dev, local_rank, parity_device):
+    """configs[2]: the same cell with another model (SevenNet-l3i5): ms/step, roofline of its dominant
+    kernel, parity against the oracle."""
+    import torch
+    from sevenn_b200.checkpoint import load_weights
+    from sevenn_b200.engine import B200Engine
+    meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{model}.npz'))
+    tm = {int(k): int(v) for k, v in meta['type_map'].items()}
+    pos, cell, z, ei, ev = make_system(cells)
+    species = np.array([tm[int(a)] for a in z], dtype=np.int32)
+    eng = B200Engine(meta, arrays, radial=args.radial, device=local_rank)
+    eng.set_graph(species, ei, ev)
+    for _ in range(3):
+        eng.compute()
+    ms = time_steps(torch, eng.compute, min(args.steps, 10), flush)
+    res = eng.results()
+    energy, forces = float(res['energy'].cpu()[0]), res['forces'].cpu().numpy()
+    eng.set_profiling(True)
+    for _ in range(3):
+        flush.fill_(1)
+        eng.compute()
+    torch.cuda.synchronize()
+    roof, breakdown = roofline_from_profile(eng, eng.profile(), ei.shape[1], len(z))
+    eng.set_profiling(False)
+    out = {'model': model, 'atoms': len(z), 'edges': int(ei.shape[1]), 'ms_per_step': ms, 'value': len(z) / (ms * 1e-3),
+           'unit': UNIT, 'roofline': roof, 'kernel_breakdown_ms': breakdown, 'energy_eV': energy}
+    if parity_device != 'off':
+        out['parity'] = oracle_parity(model, species, ei, ev, energy, forces, parity_device)
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_engine(args):
     import torch
     import torch.distributed as dist
@@ -307,6 +395,22 @@ def run_engine(args):
                    'what': 'host positions -> device neighbour list + graph -> energy/forces -> host'}
         eng.set_graph(species, ei, ev)
 
+    # ---- parity of the benchmarked configuration (outside the timed regions) --------------------------
+    parity, extra, standin = None, None, None
+    if world == 1:
+        eng.compute()
+        torch.cuda.synchronize()
+        res = eng.results()
+        if args.parity != 'off':
+            parity = oracle_parity(args.model, species, ei, ev, float(res['energy'].cpu()[0]), res['forces'].cpu().numpy(), args.parity)
+        if args.cells is None and args.model == 'sevennet_0' and not args.no_extras:
+            extra = {'l3i5': extra_model(args, 'sevennet_l3i5', cells, flush, dev, local_rank, 'cuda' if args.parity != 'off' else 'off')}
+            del flush
+            torch.cuda.empty_cache()
+            standin = gpu_standin(args.model, cells)
+    else:
+        parity = distributed_parity(runner, eng, meta, arrays, pos, cell, species_all, local_rank)
+
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
@@ -323,13 +427,57 @@ def run_engine(args):
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'e2e_positions': e2e_pos,
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernel_breakdown_ms': breakdown,
+            'parity': parity,
         }
+        if extra is not None:
+            line['extra'] = extra
+        if standin is not None:
+            line['gpu_standin'] = standin
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def distributed_parity(runner, eng, meta, arrays, pos, cell, species_all, local_rank):
+    """N > 1: rank 0 also evaluates the SAME global system with a single-GPU engine and compares energy
+    and forces of all atoms with the distributed result (forces gathered over NCCL).  Outside the timed
+    regions.  (The single-GPU engine itself is compared with the fp64 oracle in the N = 1 line.)"""
+    import torch
+    import torch.distributed as dist
+    from sevenn_b200.engine import B200Engine
+    from sevenn_b200.neighbors import build_graph
+    runner.compute()
+    torch.cuda.synchronize()
+    r = runner.results()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_global = len(species_all)
+    f_all = torch.zeros(n_global, 3, dtype=torch.float32, device=eng.device)
+    gids = torch.as_tensor(np.asarray(r['global_ids']), dtype=torch.long, device=eng.device)
+    f_all[gids] = r['forces']
+    dist.all_reduce(f_all)
+    e_dist = float(r['energy'].cpu()[0])
+    out = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        ei, ev = build_graph(pos, cell, True, 5.0)
+        single = B200Engine(meta, arrays, radial=eng.radial, device=local_rank)
+        single.set_graph(species_all, ei, ev)
+        single.compute()
+        torch.cuda.synchronize()
+        rs = single.results()
+        dE = e_dist - float(rs['energy'].cpu()[0])
+        dF = float((f_all - rs['forces']).abs().max())
+        tolE, tolF = parity_tolerance(n_global)
+        out = {'against': 'the same global system evaluated by this engine on ONE GPU (rank 0)', 'dE_eV': dE,
+               'max_dF_eV_per_A': dF, 'dE_per_atom_eV': dE / n_global, 'tol_dE_eV': tolE, 'tol_dF_eV_per_A': tolF,
+               'ok': bool(abs(dE) <= tolE and dF <= tolF), 'seconds': time.perf_counter() - t0}
+        del single
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return out
 
 
 def roofline_from_profile(eng, prof, n_edges, n_dst):
@@ -353,8 +501,11 @@ def roofline_from_profile(eng, prof, n_edges, n_dst):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
-    out = {'kernel': name, 'ms': ms, 'bound': 'hbm', 'achieved': None, 'peak': peak, 'unit': 'GB/s', 'frac': None,
-           'traffic': None, 'peak_source': src}
+    sm_mhz = float(peaks.get('sm_max_mhz', 1965.0))
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    out = {'kernel': name, 'ms': ms, 'bound': 'fp32', 'achieved': None, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': None,
+           'traffic': None, 'peak_source': f'FP32 FMA pipe: 148 SM x 128 lanes x 2 flop x {sm_mhz:.0f} MHz (theoretical; '
+                                           f'MEASURED_PEAKS.json holds no fp32 entry)'}
     if name.startswith('conv_'):
         import importlib.util
         spec_ = importlib.util.spec_from_file_location('gen_kernels', os.path.join(ROOT, 'sevenn_b200', 'csrc', 'gen_kernels.py'))
@@ -375,21 +526,20 @@ def roofline_from_profile(eng, prof, n_edges, n_dst):
         l2 = (4 * (2 * l1 + 1) * mul + (12 if eng.radial == 'table' else 4) * npath * mul
               + (4 * (2 * l1 + 1) * mul if (bwd and t > 0) else 0)) * n_edges
         flops = ((f_bwd + 15 * npath) if bwd else (f_fwd + 6 * npath)) * mul * n_edges
-        sm_mhz = float(peaks.get('sm_max_mhz', 1965.0))
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        out.update(achieved=hbm / (ms * 1e-3) / 1e9, algorithmic_bytes=int(hbm))
-        out['frac'] = out['achieved'] / peak
+        out.update(achieved=flops / (ms * 1e-3) / 1e12, algorithmic_flops=int(flops))
+        out['frac'] = out['achieved'] / fp32_peak
+        out['hbm'] = {'achieved_gbs': hbm / (ms * 1e-3) / 1e9, 'peak_gbs': peak, 'frac': hbm / (ms * 1e-3) / 1e9 / peak,
+                      'algorithmic_bytes': int(hbm), 'peak_source': src}
         out['l2_gbs'] = (hbm + l2) / (ms * 1e-3) / 1e9
-        out['fp32'] = {'achieved_tflops': flops / (ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
-                       'frac': flops / (ms * 1e-3) / 1e12 / fp32_peak}
         try:   # dram bytes per launch of this kernel kind from the committed ncu --set full capture (mid layers, 12k atoms)
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
             if 1 <= t <= 3 and n_dst == 12000:
-                out['traffic'] = tr.get('sevennet_0' if eng.spec.lmax_filter == 2 else 'none', {}).get(f'{parts[0]}.l{l1}')
+                out['traffic'] = tr.get('sevennet_0' if eng.spec.lmax_filter == 2 else 'sevennet_l3i5', {}).get(f'{parts[0]}.l{l1}')
         except Exception:
             pass
-        out['note'] = ('not HBM-bound: x and the radial tables are L2-resident; ncu (profiles/) shows the FP32 '
-                       'pipe and L1/L2 latency as the limiters; traffic = ncu dram bytes per launch from profiles/ncu_traffic.json')
+        out['note'] = ('bound = the FP32 FMA pipe: the channel-wise Clebsch-Gordan product is not GEMM-shaped (DESIGN.md 4); x and the '
+                       'radial tables are L2-resident, so the HBM fraction (`hbm`) is small by construction; traffic = ncu dram '
+                       'bytes per launch from profiles/ncu_traffic.json')
     return out, breakdown
 
 
@@ -424,6 +574,9 @@ def main():
     ap.add_argument('--radial', default='table', choices=['table', 'mlp'])
     ap.add_argument('--cells', type=int, nargs=3, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--parity', default='cuda', choices=['cuda', 'cpu', 'off'],
+                    help='where the fp64 oracle of the one-off parity check runs (it is the checker, never timed)')
+    ap.add_argument('--no-extras', action='store_true', help='skip the l3i5 / gpu_standin legs of the N = 1 line')
     args = ap.parse_args()
     if args.gpus not in CELLS:
         raise SystemExit('--gpus must be 1, 2, 4 or 8')

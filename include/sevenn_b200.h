@@ -102,6 +102,11 @@ S7B_API int s7b_dense_linear(const float* A, const float* W, float* C, int64_t r
 S7B_API int s7b_engine_create(const S7bModelDesc* desc, S7bEngine** out);
 S7B_API void s7b_engine_destroy(S7bEngine* eng);
 
+/* Per engine: also fill the buffer "atomic_virial" [n_nodes, 6] (force_output.py:198-214) from the next
+ * s7b_engine_set_graph on.  (The process-wide option "atomic_virial" only sets the default of engines
+ * created afterwards; this call is the thread-safe way.) */
+S7B_API int s7b_engine_set_atomic_virial(S7bEngine* eng, int enable);
+
 /* Upload one named parameter array (host pointer, fp32).  Names: "embed_x0", "embed_g0",
  * "readout", "scale", "shift", "bessel", and per layer t "si1", "si1T", "sc", "scT", "si2",
  * "si2T", "table", "mlp0".."mlp2", "mlp0T".."mlp2T" (layouts: sevenn_b200/engine.py). */

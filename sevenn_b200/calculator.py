@@ -111,7 +111,9 @@ class SevenNetCalculator(_Base):
         # neighbour list, graph build, model and force path all run on the GPU (one C-ABI call);
         # the reference builds the graph on the CPU every step (calculator.py:224-226)
         energy, energies, forces, virial, n_edges = self.engine.compute_positions(species, pos, cell, pbc)
-        vol = abs(np.linalg.det(cell)) if pbc.all() else 0.0
+        # the reference divides by atoms.cell.volume whatever the pbc flags are (dataload.py:121,
+        # force_output.py:227-228); a missing cell (volume 0) has no stress
+        vol = abs(np.linalg.det(cell))
         self.results = {
             'free_energy': energy, 'energy': energy,
             'energies': energies.astype(np.float64),

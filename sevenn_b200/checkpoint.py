@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import io
 import json
+import os
 from typing import Dict, Tuple
 
 import numpy as np
@@ -45,7 +46,20 @@ def convert_reference_checkpoint(path: str, name: str) -> Tuple[dict, Dict[str, 
     the files pickle only tensors and builtins) and return ``(meta, arrays)``."""
     import torch
 
-    ck = torch.load(path, map_location='cpu', weights_only=False)
+    try:       # the files hold tensors, builtins and a few numpy scalars/arrays: the restricted unpickler
+        # with numpy's array reconstruction allow-listed is enough (no arbitrary code execution)
+        import numpy._core.multiarray as ma
+        allow = [(ma._reconstruct, 'numpy.core.multiarray._reconstruct'), (ma.scalar, 'numpy.core.multiarray.scalar'),
+                 ma._reconstruct, ma.scalar, np.ndarray, np.dtype]
+        allow += [type(np.dtype(t)) for t in ('f4', 'f8', 'i4', 'i8', 'b1', 'U1', 'S1')]
+        with torch.serialization.safe_globals(allow):
+            ck = torch.load(path, map_location='cpu', weights_only=True)
+    except Exception as ex:   # noqa: BLE001
+        if os.environ.get('S7B_UNSAFE_LOAD') != '1':
+            raise RuntimeError(
+                f'{path}: torch.load(weights_only=True) failed ({type(ex).__name__}: {ex}); if you trust the file, '
+                f'set S7B_UNSAFE_LOAD=1 to allow full unpickling') from ex
+        ck = torch.load(path, map_location='cpu', weights_only=False)
     cfg, sd = ck['config'], ck['model_state_dict']
     version = str(cfg['version'])
     vt = _version_tuple(version)

@@ -55,7 +55,8 @@ __global__ void edge_fwd_kernel(const RadialDesc rd, const float* __restrict__ e
   if (e >= *n_edges_p) return;
   const float vx = edge_vec[3 * e], vy = edge_vec[3 * e + 1], vz = edge_vec[3 * e + 2];
   const float r = sqrtf(vx * vx + vy * vy + vz * vz);
-  const float ir = 1.0f / r;
+  // r == 0 (a caller's degenerate pair) has no direction: harmonics of the zero vector, no NaN downstream
+  const float ir = r > 0.0f ? 1.0f / r : 0.0f;
   float Y[SH<LMAX>::NY];
   SH<LMAX>::eval(vx * ir, vy * ir, vz * ir, Y);
   float* yrow = Yout + e * ny_stride;
@@ -65,7 +66,9 @@ __global__ void edge_fwd_kernel(const RadialDesc rd, const float* __restrict__ e
   const float s = r * rd.inv_h;
   int tk = (int)s;
   tk = tk < 0 ? 0 : (tk > rd.knots - 1 ? rd.knots - 1 : tk);
-  const float tt = s - (float)tk;
+  // edges at or beyond the cutoff sit at the end of the last interval, where the envelope has taken the
+  // weights (and, for XPLOR / polynomial cutoffs, their slope) to zero: no extrapolation of the last cubic
+  const float tt = fminf(fmaxf(s - (float)tk, 0.0f), 1.0f);
   rec[e] = make_int4(__ldg(src + e), tk, __float_as_int(tt), 0);
   rlen[e] = r;
   if (emb != nullptr) {
@@ -89,7 +92,7 @@ __global__ void edge_bwd_kernel(const RadialDesc rd, const float* __restrict__ e
   if (e >= *n_edges_p) return;
   const float vx = edge_vec[3 * e], vy = edge_vec[3 * e + 1], vz = edge_vec[3 * e + 2];
   const float r = sqrtf(vx * vx + vy * vy + vz * vz);
-  const float ir = 1.0f / r;
+  const float ir = r > 0.0f ? 1.0f / r : 0.0f;
   const float ux = vx * ir, uy = vy * ir, uz = vz * ir;
   float gY[SH<LMAX>::NY];
   gY[0] = 0.0f;

@@ -602,6 +602,13 @@ void s7b_engine_destroy(S7bEngine* e) {
   delete e;
 }
 
+int s7b_engine_set_atomic_virial(S7bEngine* e, int enable) {
+  if (!e) return fail("null engine");
+  if (e->want_atomic_virial != (enable != 0)) ++g_alloc_gen;   // a captured step graph bakes the choice in
+  e->want_atomic_virial = enable != 0;
+  return 0;
+}
+
 int s7b_engine_set_param(S7bEngine* e, const char* name, int layer, const float* host, size_t numel) {
   if (!e || !name || !host) return fail("null argument");
   const std::string nm(name);

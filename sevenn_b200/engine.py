@@ -47,6 +47,7 @@ class S7bModelDesc(ctypes.Structure):
 
 EXPORTS = [
     's7b_last_error', 's7b_version', 's7b_set_option', 's7b_dense_linear', 's7b_engine_create', 's7b_engine_destroy',
+    's7b_engine_set_atomic_virial',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
     's7b_engine_buffer', 's7b_engine_compute_host', 's7b_engine_set_positions_host',
     's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_graph_stats', 's7b_engine_set_profiling',
@@ -72,6 +73,7 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_engine_create.argtypes = [ctypes.POINTER(S7bModelDesc), ctypes.POINTER(vp)]
     lib.s7b_engine_destroy.argtypes = [vp]
     lib.s7b_engine_destroy.restype = None
+    lib.s7b_engine_set_atomic_virial.argtypes = [vp, ctypes.c_int]
     lib.s7b_engine_set_param.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, vp, sz]
     lib.s7b_engine_set_graph.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp]
     lib.s7b_engine_run_stage.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
@@ -292,9 +294,8 @@ class B200Engine:
         self._h = ctypes.c_void_p()
         self.atomic_virial = bool(atomic_virial)
         with torch.cuda.device(self.device):
-            set_option('atomic_virial', 1 if atomic_virial else 0)
             check(self.lib.s7b_engine_create(ctypes.byref(d), ctypes.byref(self._h)))
-            set_option('atomic_virial', 0)
+            check(self.lib.s7b_engine_set_atomic_virial(self._h, 1 if atomic_virial else 0))
             for (name, t), arr in prepare_params(spec, arrays, radial, self.knots).items():
                 check(self.lib.s7b_engine_set_param(self._h, name.encode(), t, arr.ctypes.data, arr.size))
         self._graph = None

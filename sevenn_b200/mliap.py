@@ -109,16 +109,19 @@ class SevenNetMLIAPWrapper(_Base):
         eng.run_stage(STAGE_FWD_BEGIN)
         for t in range(T):
             eng.run_stage(STAGE_FWD_LAYER, t)
-            if t + 1 < T and ntotal > nlocal:
+            if t + 1 < T:
+                # called on EVERY rank and layer, as the reference does (mliap.py:176-247 wraps every
+                # convolution): forward_exchange is LAMMPS forward_comm, a collective over the ranks -- a
+                # rank without ghosts may still own atoms that are ghosts elsewhere and must post its sends
                 buf, out = exchanged('x', t + 1, spec.layers[t + 1].dim_x, lmp_data.forward_exchange)
-                buf[nlocal:] = out[nlocal:]            # ghost rows <- their owners' features
+                if ntotal > nlocal:
+                    buf[nlocal:] = out[nlocal:]        # ghost rows <- their owners' features
         eng.run_stage(STAGE_FWD_END)
         for t in range(T - 1, -1, -1):
             eng.run_stage(STAGE_BWD_LAYER_A, t)
             if t > 0:
-                if ntotal > nlocal:
-                    buf, out = exchanged('dx', t, spec.layers[t].dim_x, lmp_data.reverse_exchange)
-                    buf[:nlocal] = out[:nlocal]        # owners <- own + ghost-row contributions
+                buf, out = exchanged('dx', t, spec.layers[t].dim_x, lmp_data.reverse_exchange)   # reverse_comm: collective too
+                buf[:nlocal] = out[:nlocal]            # owners <- own + ghost-row contributions
                 eng.run_stage(STAGE_BWD_LAYER_B, t)
         eng.run_stage(STAGE_BWD_END)
 

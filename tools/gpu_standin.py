@@ -12,6 +12,7 @@ from sevenn_b200.neighbors import build_graph, diamond_si
 torch.backends.cuda.matmul.allow_tf32 = False
 name = sys.argv[1] if len(sys.argv) > 1 else 'sevennet_0'
 cells = tuple(int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (10, 10, 15)
+as_json = '--json' in sys.argv
 meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{name}.npz'))
 tm = {int(k): int(v) for k, v in meta['type_map'].items()}
 pos, cell, z = diamond_si(*cells)
@@ -27,6 +28,14 @@ for _ in range(5):
     out = o.forward(sp, ei, ev)
     torch.cuda.synchronize()
     ts.append(time.perf_counter() - t0)
+if as_json:
+    import json
+    print(json.dumps({'what': 'torch-CUDA fp32 unfused stand-in of the reference GPU path (oracle restatement executed with stock '
+                              'torch CUDA ops + autograd; the e3nn path itself cannot be installed here)',
+                      'model': name, 'atoms': len(z), 'edges': int(ei.shape[1]), 'ms_per_step': 1e3 * min(ts),
+                      'value': len(z) / min(ts), 'unit': 'atom-updates/s', 'best_of': len(ts),
+                      'peak_mem_GiB': torch.cuda.max_memory_allocated() / 2**30, 'energy_eV': float(out['energy'])}))
+    sys.exit(0)
 print(f'{name} {len(z)} atoms {ei.shape[1]} edges: torch-CUDA fp32 unfused stand-in {1e3*min(ts):.1f} ms/step '
       f'(best of 5) = {len(z)/min(ts):.0f} atom-updates/s; E = {float(out["energy"]):.3f} eV; '
       f'peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB')
