@@ -268,7 +268,7 @@ def run_engine(args):
         dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     from sevenn_b200.engine import set_option
-    for opt in ('concurrent_conv', 'tc_gemm', 'cuda_graph'):   # A/B switches: S7B_CONCURRENT_CONV=0, S7B_TC_GEMM=1, S7B_CUDA_GRAPH=0
+    for opt in ('concurrent_conv', 'tc_gemm', 'cuda_graph', 'tc_swizzle'):   # A/B switches: S7B_CONCURRENT_CONV=0, S7B_TC_GEMM=1, S7B_CUDA_GRAPH=0
         if os.environ.get('S7B_' + opt.upper()) is not None:
             set_option(opt, int(os.environ['S7B_' + opt.upper()]))
     meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{args.model}.npz'))
@@ -296,7 +296,7 @@ def run_engine(args):
         part = brick_decompose(pos, cell, species_all, GRIDS[args.gpus], rank, 5.0)
         n_edges_local = part['edge_index'].shape[1]
         eng = B200Engine(meta, arrays, radial=args.radial, device=local_rank)
-        runner = DistributedRunner(eng, part)
+        runner = DistributedRunner(eng, part, cuda_graph=bool(int(os.environ.get('S7B_CUDA_GRAPH', '1'))))
         t = torch.tensor([n_edges_local], device=dev, dtype=torch.int64)
         dist.all_reduce(t)
         n_edges = int(t.item())
@@ -336,6 +336,9 @@ def run_engine(args):
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) ---------------------------
     # (every rank runs the same steps -- the exchanges are collective; only rank 0 records events)
     roofline, breakdown = None, None
+    if runner is not None:
+        graph_on = runner.use_graph
+        runner.set_cuda_graph(False)      # per-kernel events need the eager stage sequence
     eng.set_profiling(rank == 0)
     for _ in range(min(args.steps, 10)):
         flush.fill_(1)
@@ -345,6 +348,8 @@ def run_engine(args):
         prof = eng.profile()
         roofline, breakdown = roofline_from_profile(eng, prof, n_edges if world == 1 else n_edges_local, eng.n_local)
     eng.set_profiling(False)
+    if runner is not None:
+        runner.set_cuda_graph(graph_on)
 
     # ---- end to end through the host-buffer entry (N = 1) or the runner's host path (N > 1) -------
     if world == 1:
@@ -422,7 +427,10 @@ def run_engine(args):
                 'weights': f'{args.model} converted from the reference checkpoint', 'radial': args.radial,
                 'parallelism': 'single GPU' if world == 1 else f'spatial bricks {GRIDS[args.gpus]} + NCCL ghost exchange',
                 'l2': 'flushed with a 256 MiB write between timed steps',
-                'cuda_graph': bool(int(os.environ.get('S7B_CUDA_GRAPH', '1'))) and world == 1 and args.radial == 'table',
+                'cuda_graph': (bool(int(os.environ.get('S7B_CUDA_GRAPH', '1'))) and args.radial == 'table') if world == 1
+                else bool(runner.use_graph and runner.graph_replays > 0),
+                'cuda_graph_note': None if world == 1 else (runner.graph_error or f'{runner.graph_captures} capture(s), {runner.graph_replays} replays; NCCL calls inside the graph'),
+                'tc_gemm': bool(int(os.environ.get('S7B_TC_GEMM', '1'))),
                 'energy_eV': float(out[0]) if world == 1 else float(out['energy'])},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'e2e_positions': e2e_pos,

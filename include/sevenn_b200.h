@@ -77,15 +77,24 @@ enum {
   S7B_STAGE_FWD_LAYER_A = 6,
   S7B_STAGE_FWD_LAYER_SC = 7,
   S7B_STAGE_BWD_LAYER_B1 = 8,
-  S7B_STAGE_BWD_LAYER_B2 = 9
+  S7B_STAGE_BWD_LAYER_B2 = 9,
+  /* interior / boundary split of the convolutions (s7b_engine_set_interior): owned atoms [0, n_interior)
+   * have no ghost neighbour.  FWD_LAYER_A(t) = FWD_CONV_INTERIOR(t) + FWD_LAYER_A2(t): the interior
+   * convolution needs no ghost row of x(t) and runs while they are still in flight.
+   * BWD_LAYER_A(t) = BWD_LAYER_A1(t) + BWD_LAYER_A2(t): A1 ends with the boundary atoms' backward
+   * convolution, after which the ghost rows of dx(t) are final and can travel while A2 (interior) runs. */
+  S7B_STAGE_FWD_CONV_INTERIOR = 10,
+  S7B_STAGE_FWD_LAYER_A2 = 11,
+  S7B_STAGE_BWD_LAYER_A1 = 12,
+  S7B_STAGE_BWD_LAYER_A2 = 13
 };
 
 S7B_API const char* s7b_last_error(void);
 S7B_API int s7b_version(void);
 
-/* Runtime options: "tc_gemm" = 1 runs the node linears on tcgen05 tensor cores (3xTF32 with TMEM
- * accumulators; ~5e-7 relative error with a small systematic component from the tensor core's
- * truncating accumulation); 0 (default) selects the FP32 SIMT GEMM kernel (IEEE fp32 FMA chain).
+/* Runtime options: "tc_gemm" = 1 (default) runs the node linears on tcgen05 tensor cores (TMA-fed,
+ * TMEM accumulators, error-free bf16x3 fixed-point slices: sevenn_b200/csrc/tc_gemm.cuh); 0 selects the
+ * FP32 SIMT GEMM kernel (IEEE fp32 FMA chain).  "tc_swizzle" (default 1): 128B-swizzled TMA tiles.
  * "atomic_virial" = 1: engines created afterwards also fill the buffer "atomic_virial" [n_nodes, 6]
  * (force_output.py:198-214).  "concurrent_conv" (default 1): co-schedule the per-l1 convolution kernels.
  * "cuda_graph" (default 1): s7b_engine_compute (and the two *_host entry points built on it) replay a
@@ -97,6 +106,21 @@ S7B_API int s7b_set_option(const char* name, int value);
  * engine uses for its linears; use_tc selects the tcgen05 path (needs K % 32 == 0, N % 16 == 0). */
 S7B_API int s7b_dense_linear(const float* A, const float* W, float* C, int64_t rows, int32_t K, int32_t N,
                              int32_t use_tc, void* stream);
+
+/* Ghost-exchange pack / unpack for multi-GPU callers (device pointers; the transfer itself is the caller's:
+ * NCCL send/recv in sevenn_b200/parallel.py).  Replaces the pack/unpack loops of
+ * sevenn/pair_e3gnn/pair_e3gnn_parallel.cpp:698-799.
+ *   gather:      out[i, :width] = src[idx[i], :width]           (out packed [n, width])
+ *   scatter_add: dst[idx[i], :width] += in[i, :width]           (idx unique within one call) */
+S7B_API int s7b_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t n, int32_t width,
+                            float* out, void* stream);
+S7B_API int s7b_scatter_add_rows(float* dst, int32_t ld_dst, const int32_t* idx, int64_t n, int32_t width,
+                                 const float* in, void* stream);
+
+/* Host-only helper (no GPU needed): the weight packing of the tensor-core linear for one [K, N] block --
+ * three signed 8-bit fixed-point slices per weight as bf16, in the shared-memory layout the kernel
+ * consumes (sevenn_b200/csrc/tc_gemm.cuh).  q: 3*K*N uint16, fb: N column scales, *NT: tile width. */
+S7B_API int s7b_tc_pack_weights(const float* W, int32_t K, int32_t N, uint16_t* q, float* fb, int32_t* NT);
 
 /* ---- engine ---------------------------------------------------------------------------- */
 S7B_API int s7b_engine_create(const S7bModelDesc* desc, S7bEngine** out);
@@ -118,6 +142,10 @@ S7B_API int s7b_engine_set_param(S7bEngine* eng, const char* name, int layer, co
 S7B_API int s7b_engine_set_graph(S7bEngine* eng, int32_t n_nodes, int32_t n_local, int64_t n_edges,
                          const int32_t* d_species, const int32_t* d_rowptr, const int32_t* d_src,
                          const float* d_edge_vec, void* stream);
+
+/* Number of leading owned atoms without ghost neighbours (default: n_local, i.e. no boundary range);
+ * call after s7b_engine_set_graph.  Only the split stages 10-13 look at it. */
+S7B_API int s7b_engine_set_interior(S7bEngine* eng, int32_t n_interior);
 
 S7B_API int s7b_engine_run_stage(S7bEngine* eng, int stage, int layer, void* stream);
 S7B_API int s7b_engine_compute(S7bEngine* eng, void* stream);

@@ -41,7 +41,7 @@ struct ConvArgs {
   const float4* table;        // [knots, W/2] {a0e,a0o,a1e,a1o}: value and slope*h of the cubic, per channel pair
   const uint2* table23;       // [knots, W/2] {half2(a2e,a2o), half2(a3e,a3o)}: the two small cubic terms in fp16
   const float* w;             // [E, W] stored weights (operator boundary / exact-MLP mode)
-  int n_dst;
+  int n_begin, n_dst;        // centre atoms [n_begin, n_dst) of this launch (multi-GPU: interior / boundary ranges)
   int dim_x, dim_mid, w_numel, ny_stride;
   float inv_h;                // 1 / table interval
 };

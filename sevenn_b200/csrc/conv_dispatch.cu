@@ -17,6 +17,7 @@ int64_t g_conv_launches = 0;
 
 int launch_conv_fwd(int l1, int lf, int lo, bool table, const ConvArgs& a, const ConvRole& role,
                     float* out, cudaStream_t st) {
+  if (a.n_dst <= a.n_begin) return 0;      // empty centre range
   int rc = 2;
   if (lf == 2 && lo == 2) rc = launch_conv_fwd_2_2(l1, table, a, role, out, st);
   else if (lf == 2 && lo == 0) rc = launch_conv_fwd_2_0(l1, table, a, role, out, st);
@@ -31,6 +32,7 @@ int launch_conv_fwd(int l1, int lf, int lo, bool table, const ConvArgs& a, const
 int launch_conv_bwd(int l1, int lf, int lo, bool table, bool need_dx, const ConvArgs& a,
                     const ConvRole& role, const float* gout, float* dx, float* dY_acc,
                     float* dEdr_acc, float* dw, cudaStream_t st) {
+  if (a.n_dst <= a.n_begin) return 0;      // empty centre range
   int rc = 2;
   if (lf == 2 && lo == 2) rc = launch_conv_bwd_2_2(l1, table, need_dx, a, role, gout, dx, dY_acc, dEdr_acc, dw, st);
   else if (lf == 2 && lo == 0) rc = launch_conv_bwd_2_0(l1, table, need_dx, a, role, gout, dx, dY_acc, dEdr_acc, dw, st);

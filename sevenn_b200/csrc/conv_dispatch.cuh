@@ -22,7 +22,7 @@ namespace s7b {
 template <int LPN>
 static inline dim3 conv_grid(const ConvArgs& a, const ConvRole& role, int nv) {
   const int nodes_per_block = kConvWarpsPerBlock * (32 / LPN);
-  return dim3((a.n_dst + nodes_per_block - 1) / nodes_per_block, role.mul / (2 * LPN * nv));
+  return dim3((a.n_dst - a.n_begin + nodes_per_block - 1) / nodes_per_block, role.mul / (2 * LPN * nv));
 }
 
 template <class Kind, int NV, int LPN>
@@ -36,7 +36,7 @@ static int launch_fwd_one(bool table, const ConvArgs& a, const ConvRole& role, f
 // one channel per lane, a full warp per node (alternative forward mapping for mul = 32, see S7B_FWD_ODD_PAIRS)
 template <class Kind>
 static int launch_fwd_scalar(bool table, const ConvArgs& a, const ConvRole& role, float* out, cudaStream_t st) {
-  dim3 grid((a.n_dst + kConvWarpsPerBlock - 1) / kConvWarpsPerBlock, role.mul / 32);
+  dim3 grid((a.n_dst - a.n_begin + kConvWarpsPerBlock - 1) / kConvWarpsPerBlock, role.mul / 32);
   if (table) conv_fwd_kernel<Kind, 1, 32, true, float><<<grid, 32 * kConvWarpsPerBlock, 0, st>>>(a, role, out);
   else conv_fwd_kernel<Kind, 1, 32, false, float><<<grid, 32 * kConvWarpsPerBlock, 0, st>>>(a, role, out);
   return cudaGetLastError() == cudaSuccess ? 0 : 1;

@@ -160,7 +160,7 @@ struct LaneMap {
     constexpr int GPW = 32 / LPN;
     const int lane = threadIdx.x & 31;
     sl = lane % LPN;
-    n = (blockIdx.x * kConvWarpsPerBlock + (threadIdx.x >> 5)) * GPW + lane / LPN;
+    n = a.n_begin + (blockIdx.x * kConvWarpsPerBlock + (threadIdx.x >> 5)) * GPW + lane / LPN;
     node_ok = n < a.n_dst;
     uc0 = blockIdx.y * (CH * LPN * NV) + CH * sl;
     e0 = 0;

@@ -139,6 +139,13 @@ struct LayerCfg {
   ConvRole roles[kMaxL];
   GateDesc gate;
   std::map<std::string, DevBuf> params;
+  std::map<std::string, struct TcWeights*> tcw;   // tensor-core form of si1/si1T/sc/scT/si2/si2T (engine.cu: TcWeights)
+};
+
+// Row exponents of a GEMM input (tc_gemm.cuh): E[n, row_base[l] + i]
+struct RowExp {
+  DevBuf buf;
+  int rows_per_node = 0;
 };
 
 }  // namespace s7b
@@ -153,7 +160,7 @@ struct S7bEngine {
   bool radial_ready = false;
   int ny_stride = 8;
   // graph
-  int n_nodes = 0, n_local = 0;
+  int n_nodes = 0, n_local = 0, n_interior = 0;
   int64_t n_edges = 0;
   const int* d_species = nullptr;
   const int* d_rowptr = nullptr;
@@ -163,6 +170,7 @@ struct S7bEngine {
   DevBuf rec, Y, rlen, emb, dY_acc, dEdr_acc, demb_acc, fedge;
   std::vector<DevBuf> x, g, wbuf, z1, z2, h1, h2;   // per layer (wbuf.. exact-MLP mode only)
   DevBuf mid, h, dh, dg, dx, dwbuf, tmpA, tmpB;
+  RowExp re_mid, re_h, re_dg, re_dx;      // row exponents of the tensor-core GEMM inputs
   DevBuf energy, atomic_energy, forces, virial, atomic_virial;
   bool want_atomic_virial = false;
   // host staging for compute_host
@@ -301,17 +309,8 @@ static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* 
 static int g_opt_atomic_virial = 0;   // engines created afterwards also produce the per-atom virial
 static int g_opt_concurrent = 1;   // co-schedule the per-l1 convolution kernels of a layer on side streams
 static int g_opt_cuda_graph = 1;   // s7b_engine_compute replays a captured CUDA graph of the step (table mode)
-static int g_opt_tc_gemm = 0;   // 1: node linears on tcgen05 (3xTF32); default FP32 SIMT
-
-// hi = rna_tf32(w), lo = rna_tf32(w - hi)   (see tc_gemm.cuh)
-__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float v = w[i];
-    const float h = rna_tf32(v);
-    hi[i] = h;
-    lo[i] = rna_tf32(v - h);
-  }
-}
+static int g_opt_tc_gemm = 1;   // 1 (default): node linears on tcgen05 (error-free bf16x3 slices, tc_gemm.cuh); 0: FP32 SIMT
+static int g_opt_tc_swizzle = 1;   // 128B-swizzled TMA tile for the raw A chunk (0: plain rows; A/B switch)
 
 __global__ void set_i64_kernel(int64_t* p, int64_t v) { *p = v; }
 
@@ -342,22 +341,199 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
-static int launch_tc_gemm(const TcLinArgs& a, cudaStream_t st) {
-  int max_rows = 0, max_n = 0;
-  for (int b = 0; b < a.nblocks; ++b) {
-    max_rows = std::max(max_rows, a.n_nodes * a.blk[b].d);
-    max_n = std::max(max_n, a.blk[b].N);
+// ---- tensor-core linear: host side --------------------------------------------------------------
+// Pre-sliced weights of one block-diagonal linear (see tc_gemm.cuh): per block l the three bf16 slices of
+// W^T in the canonical K-major UMMA layout, cut into (n tile, 32-wide K chunk) blobs that one
+// cp.async.bulk moves into a pipeline stage, plus the per-column scales 2^(Eb-7).
+struct TcWeights {
+  DevBuf q, fb;
+  int nblocks = 0;
+  bool ok = false;
+  struct Blk { int K, N, NT; size_t q_off, fb_off; } blk[kMaxL];
+};
+
+static int tc_pick_nt(int N) {
+  if (N % 16 != 0) return 0;
+  if (N <= kTcMaxNT) return N;
+  for (int c = 2; c <= 16; ++c)
+    if (N % c == 0 && (N / c) % 16 == 0 && N / c <= kTcMaxNT) return N / c;
+  return 0;
+}
+
+static inline uint16_t bf16_bits_exact(float v) {   // v has <= 8 significant bits: truncation is exact
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  return (uint16_t)(u >> 16);
+}
+
+// W [K, N] row-major (fp32) -> q [(N/NT) * (K/32) * 3 * NT*32] bf16 bits, fb [N].  Host only.
+static void tc_pack_block(const float* W, int K, int N, int NT, uint16_t* q, float* fb) {
+  const int n_kc = K / kTcKC, n_nt = N / NT;
+  for (int n = 0; n < N; ++n) {
+    double amax = 0.0;
+    for (int k = 0; k < K; ++k) amax = std::max(amax, (double)fabsf(W[(size_t)k * N + n]));
+    int Eb = 0;
+    const bool zero = !(amax > 1e-30);
+    if (!zero) frexp(amax, &Eb);                       // amax = m * 2^Eb, m in [0.5, 1)  =>  amax < 2^Eb
+    fb[n] = zero ? 0.0f : (float)ldexp(1.0, Eb - 7);
+    const int nt = n / NT, r = n % NT;
+    for (int k = 0; k < K; ++k) {
+      double sl[3] = {0.0, 0.0, 0.0};
+      if (!zero) {
+        const double t = ldexp((double)W[(size_t)k * N + n], 23 - Eb);     // |t| < 2^23, exact
+        const double q0 = nearbyint(t / 65536.0);
+        const double r1 = t - q0 * 65536.0;
+        const double q1 = nearbyint(r1 / 256.0);
+        const double r2 = r1 - q1 * 256.0;
+        const double q2 = nearbyint(r2);
+        sl[0] = q0; sl[1] = q1 / 256.0; sl[2] = q2 / 65536.0;
+      }
+      const int kc = k / kTcKC, kk = k % kTcKC;
+      const size_t elem = (size_t)((r & 7) * 16 + (r >> 3) * 512 + (kk >> 3) * 128 + (kk & 7) * 2) / 2;
+      for (int sidx = 0; sidx < 3; ++sidx)
+        q[(((size_t)nt * n_kc + kc) * 3 + sidx) * ((size_t)NT * kTcKC) + elem] = bf16_bits_exact((float)sl[sidx]);
+    }
   }
-  if (max_rows == 0 || max_n == 0) return 0;
-  const int n_chunk = std::min(max_n, kTcMaxN);
-  const size_t smem = 2 * (2 * 16384 + 2 * (size_t)n_chunk * 128);
-  static size_t configured = 0;
-  if (smem > configured) {
-    S7B_CUDA_CHECK(cudaFuncSetAttribute(blocklin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  (void)n_nt;
+}
+
+static int tc_build_weights(TcWeights& w, const float* host, const int* Ks, const int* Ns, int n_l) {
+  w.ok = false;
+  w.nblocks = 0;
+  size_t q_total = 0, fb_total = 0, woff = 0;
+  for (int l = 0; l < n_l; ++l) {
+    const int K = Ks[l], N = Ns[l];
+    if (K == 0 || N == 0) continue;
+    const int NT = tc_pick_nt(N);
+    if (NT == 0 || K % kTcKC != 0) return 0;          // not expressible: caller keeps the SIMT kernel
+    TcWeights::Blk& b = w.blk[w.nblocks++];
+    b = {K, N, NT, q_total, fb_total};
+    q_total += (size_t)3 * K * N;
+    fb_total += (size_t)N;
   }
-  dim3 grid((max_rows + kTcBM - 1) / kTcBM, (max_n + n_chunk - 1) / n_chunk, a.nblocks);
-  blocklin_tc_kernel<<<grid, kTcThreads, smem, st>>>(a, n_chunk);
+  std::vector<uint16_t> q(q_total);
+  std::vector<float> fb(fb_total);
+  int bi = 0;
+  for (int l = 0; l < n_l; ++l) {
+    const int K = Ks[l], N = Ns[l];
+    if (K == 0 || N == 0) continue;
+    const TcWeights::Blk& b = w.blk[bi++];
+    tc_pack_block(host + woff, K, N, b.NT, q.data() + b.q_off, fb.data() + b.fb_off);
+    woff += (size_t)K * N;
+  }
+  if (w.q.ensure(q_total * sizeof(uint16_t) + 16) || w.fb.ensure(fb_total * sizeof(float) + 16)) return fail("cudaMalloc failed for tensor-core weights");
+  S7B_CUDA_CHECK(cudaMemcpy(w.q.p, q.data(), q_total * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  S7B_CUDA_CHECK(cudaMemcpy(w.fb.p, fb.data(), fb_total * sizeof(float), cudaMemcpyHostToDevice));
+  w.ok = true;
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else cudaGetLastError();
+  }
+  return fn;
+}
+
+static int launch_row_exponents(RowExp& re, const float* A, int lda, const int* a_off, const int* a_K, int n_l,
+                                int n_nodes, cudaStream_t st) {
+  RowExpArgs r;
+  memset(&r, 0, sizeof(r));
+  r.A = A;
+  r.lda = lda;
+  r.n_nodes = n_nodes;
+  int rows = 0;
+  for (int l = 0; l < n_l; ++l) {
+    if (a_K[l] == 0) continue;
+    if (a_K[l] % 4 != 0) return fail("row exponents need K % 4 == 0");
+    const int b = r.nblocks++;
+    r.d[b] = 2 * l + 1;
+    r.K[b] = a_K[l];
+    r.a_off[b] = a_off[l];
+    r.row_base[b] = rows;
+    rows += 2 * l + 1;
+  }
+  r.rows_per_node = rows;
+  re.rows_per_node = rows;
+  if (rows == 0 || n_nodes == 0) return 0;
+  if (re.buf.ensure((size_t)n_nodes * rows * sizeof(int))) return fail("cudaMalloc failed for row exponents");
+  r.E = re.buf.as<int>();
+  const long long total = (long long)n_nodes * rows;
+  const int blk = 256, wpb = blk / 32;
+  const int grd = (int)std::min<long long>((total + wpb - 1) / wpb, 148LL * 16);
+  row_exponent_kernel<<<grd, blk, 0, st>>>(r);
+  S7B_LAUNCH_CHECK();
+  return 0;
+}
+
+// C blocks (+)= A blocks * W blocks on the tensor cores.  A's row exponents must be current in `re`.
+// Block l of the call uses row group l of `re` (both enumerate l = 0.. over non-empty blocks).
+static int launch_tc_linear(const TcWeights& w, const RowExp& re, const float* A, int lda, const int* a_off,
+                            const int* a_K, float* C, int ldc, const int* c_off, const int* c_N, int n_l,
+                            int n_nodes, bool accumulate, cudaStream_t st) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return fail("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  TcLinArgs t;
+  TcMaps maps;
+  memset(&t, 0, sizeof(t));
+  memset(&maps, 0, sizeof(maps));
+  t.C = C;
+  t.E = re.buf.as<int>();
+  t.ldc = ldc;
+  t.n_nodes = n_nodes;
+  t.rows_per_node = re.rows_per_node;
+  t.accumulate = accumulate ? 1 : 0;
+  t.swizzle = g_opt_tc_swizzle;
+  const int n_mt = (n_nodes + kTcBM - 1) / kTcBM;
+  int tiles = 0, rows = 0, bi = 0;
+  for (int l = 0; l < n_l; ++l) {
+    if (a_K[l] == 0 || c_N[l] == 0) { if (a_K[l] != 0) rows += 2 * l + 1; continue; }
+    if (bi >= w.nblocks || w.blk[bi].K != a_K[l] || w.blk[bi].N != c_N[l]) return fail("tensor-core weights do not match the call");
+    TcLinBlock& b = t.blk[t.nblocks];
+    b.Wq = w.q.as<uint16_t>() + w.blk[bi].q_off;
+    b.fb = w.fb.as<float>() + w.blk[bi].fb_off;
+    b.d = 2 * l + 1;
+    b.K = a_K[l];
+    b.N = c_N[l];
+    b.NT = w.blk[bi].NT;
+    b.c_off = c_off[l];
+    b.c_cs = c_N[l];
+    b.row_base = rows;
+    b.tile0 = tiles;
+    tiles += n_mt * b.d * (b.N / b.NT);
+    rows += 2 * l + 1;
+    // A block viewed as (k, component, node): strides K*4 and lda*4 bytes
+    const cuuint64_t gdim[3] = {(cuuint64_t)b.K, (cuuint64_t)b.d, (cuuint64_t)n_nodes};
+    const cuuint64_t gstr[2] = {(cuuint64_t)b.K * 4, (cuuint64_t)lda * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kTcKC, 1, (cuuint32_t)kTcBM};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult cr = enc(&maps.m[t.nblocks], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)(A + a_off[l]), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, g_opt_tc_swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
+    ++t.nblocks;
+    ++bi;
+  }
+  if (tiles == 0) return 0;
+  t.n_tiles = tiles;
+  static int n_sm = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    S7B_CUDA_CHECK(cudaGetDevice(&dev));
+    S7B_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    S7B_CUDA_CHECK(cudaFuncSetAttribute(blocklin_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    configured = true;
+  }
+  blocklin_tc_kernel<<<std::min(tiles, n_sm), kTcThreads, kTcSmemBytes, st>>>(t, maps);
   S7B_LAUNCH_CHECK();
   return 0;
 }
@@ -379,39 +555,7 @@ static int launch_gemm(const LinArgs& a, cudaStream_t st) {
 // stored one after another in `W`.  A blocks: (a_off[l], K = a_K[l]); C blocks: (c_off[l], N = c_N[l]).
 static int irreps_linear(const float* A, int lda, const int* a_off, const int* a_K, float* C, int ldc,
                          const int* c_off, const int* c_N, int n_l, const float* W, int n_nodes,
-                         bool accumulate, cudaStream_t st, const float* Wt_hi = nullptr,
-                         const float* Wt_lo = nullptr) {
-  if (g_opt_tc_gemm && Wt_hi != nullptr && Wt_lo != nullptr) {
-    bool ok = true;
-    for (int l = 0; l < n_l; ++l)
-      if (a_K[l] != 0 && c_N[l] != 0 && (a_K[l] % kTcKC != 0 || c_N[l] % 16 != 0)) ok = false;
-    if (ok) {
-      TcLinArgs t;
-      memset(&t, 0, sizeof(t));
-      t.A = A;
-      t.C = C;
-      t.lda = lda;
-      t.ldc = ldc;
-      t.n_nodes = n_nodes;
-      t.accumulate = accumulate ? 1 : 0;
-      size_t woff = 0;
-      for (int l = 0; l < n_l; ++l) {
-        if (a_K[l] == 0 || c_N[l] == 0) continue;
-        TcLinBlock& b = t.blk[t.nblocks++];
-        b.Wt_hi = Wt_hi + woff;     // W^T blocks are stored in the same per-l order, [N, K] each
-        b.Wt_lo = Wt_lo + woff;
-        b.d = 2 * l + 1;
-        b.K = a_K[l];
-        b.N = c_N[l];
-        b.a_off = a_off[l];
-        b.a_cs = a_K[l];
-        b.c_off = c_off[l];
-        b.c_cs = c_N[l];
-        woff += (size_t)a_K[l] * c_N[l];
-      }
-      return launch_tc_gemm(t, st);
-    }
-  }
+                         bool accumulate, cudaStream_t st) {
   LinArgs a;
   memset(&a, 0, sizeof(a));
   a.A = A;
@@ -437,6 +581,20 @@ static int irreps_linear(const float* A, int lda, const int* a_off, const int* a
     woff += (size_t)a_K[l] * c_N[l];
   }
   return launch_gemm(a, st);
+}
+
+// One block-diagonal node linear of layer `L`, parameter `name`: tensor cores when the shapes allow it
+// (default), else the FP32 SIMT kernel.  `re` holds the row exponents of A; `fresh_re` = compute them now
+// over the n_l_A irrep blocks of A (a later call on the same A reuses them).
+static int node_linear(const LayerCfg& L, const char* name, RowExp& re, bool fresh_re, int n_l_A, const float* A,
+                       int lda, const int* a_off, const int* a_K, float* C, int ldc, const int* c_off,
+                       const int* c_N, int n_l, const float* W, int n_nodes, bool accumulate, cudaStream_t st) {
+  auto it = L.tcw.find(name);
+  if (g_opt_tc_gemm && it != L.tcw.end() && it->second && it->second->ok) {
+    if (fresh_re && launch_row_exponents(re, A, lda, a_off, a_K, n_l_A, n_nodes, st)) return 1;
+    return launch_tc_linear(*it->second, re, A, lda, a_off, a_K, C, ldc, c_off, c_N, n_l, n_nodes, accumulate, st);
+  }
+  return irreps_linear(A, lda, a_off, a_K, C, ldc, c_off, c_N, n_l, W, n_nodes, accumulate, st);
 }
 
 static int dense_gemm(const float* A, int K, float* C, int N, const float* W, int64_t rows, int epilogue,
@@ -486,10 +644,35 @@ int64_t s7b_launch_count(int reset) {
 int s7b_set_option(const char* name, int value) {
   if (!name) return fail("null option name");
   if (std::string(name) == "tc_gemm") { g_opt_tc_gemm = value; return 0; }
+  if (std::string(name) == "tc_swizzle") { g_opt_tc_swizzle = value; return 0; }
   if (std::string(name) == "atomic_virial") { g_opt_atomic_virial = value; return 0; }
   if (std::string(name) == "concurrent_conv") { g_opt_concurrent = value; return 0; }
   if (std::string(name) == "cuda_graph") { g_opt_cuda_graph = value; return 0; }
   return fail(std::string("unknown option: ") + name);
+}
+
+int s7b_gather_rows(const float* src, int32_t ld_src, const int32_t* idx, int64_t n, int32_t width, float* out, void* stream) {
+  if (n <= 0 || width <= 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = width % 4 == 0 && ld_src % 4 == 0 && (reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+  const size_t total = (size_t)n * (vec ? width / 4 : width);
+  const int grd = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  if (vec) gather_rows_idx_kernel<true><<<grd, 256, 0, st>>>(src, ld_src, idx, n, width, out);
+  else gather_rows_idx_kernel<false><<<grd, 256, 0, st>>>(src, ld_src, idx, n, width, out);
+  S7B_LAUNCH_CHECK();
+  return 0;
+}
+
+int s7b_scatter_add_rows(float* dst, int32_t ld_dst, const int32_t* idx, int64_t n, int32_t width, const float* in, void* stream) {
+  if (n <= 0 || width <= 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool vec = width % 4 == 0 && ld_dst % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(in)) % 16 == 0;
+  const size_t total = (size_t)n * (vec ? width / 4 : width);
+  const int grd = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  if (vec) scatter_add_rows_idx_kernel<true><<<grd, 256, 0, st>>>(dst, ld_dst, idx, n, width, in);
+  else scatter_add_rows_idx_kernel<false><<<grd, 256, 0, st>>>(dst, ld_dst, idx, n, width, in);
+  S7B_LAUNCH_CHECK();
+  return 0;
 }
 
 int s7b_dense_linear(const float* A, const float* W, float* C, int64_t rows, int32_t K, int32_t N,
@@ -497,28 +680,33 @@ int s7b_dense_linear(const float* A, const float* W, float* C, int64_t rows, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (rows <= 0 || K <= 0 || N <= 0 || rows > (1 << 24)) return fail("bad sizes");
   if (!use_tc) return dense_gemm(A, K, C, N, W, rows, kEpiNone, nullptr, nullptr, false, st);
-  if (K % kTcKC != 0 || N % 16 != 0) return fail("tensor-core linear needs K % 32 == 0 and N % 16 == 0");
-  float *wt = nullptr, *hi = nullptr, *lo = nullptr;
-  const size_t n = (size_t)K * N;
-  S7B_CUDA_CHECK(cudaMalloc((void**)&wt, 3 * n * sizeof(float)));
-  hi = wt + n;
-  lo = hi + n;
-  // W^T on the host side of the stream: small, done with a strided 2D copy
-  transpose_kernel<<<256, 256, 0, st>>>(W, wt, K, N);
-  split_tf32_kernel<<<256, 256, 0, st>>>(wt, hi, lo, n);
-  TcLinArgs t;
-  memset(&t, 0, sizeof(t));
-  t.A = A;
-  t.C = C;
-  t.lda = K;
-  t.ldc = N;
-  t.n_nodes = (int)rows;
-  t.nblocks = 1;
-  t.blk[0] = TcLinBlock{hi, lo, 1, K, N, 0, K, 0, N};
-  int rc = launch_tc_gemm(t, st);
+  if (K % kTcKC != 0 || tc_pick_nt(N) == 0) return fail("tensor-core linear needs K % 32 == 0 and N a multiple of 16 that splits into tiles <= 128");
+  std::vector<float> hw((size_t)K * N);
+  S7B_CUDA_CHECK(cudaMemcpyAsync(hw.data(), W, hw.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+  S7B_CUDA_CHECK(cudaStreamSynchronize(st));
+  TcWeights w;
+  RowExp re;
+  const int Ks[1] = {K}, Ns[1] = {N}, zero[1] = {0};
+  int rc = tc_build_weights(w, hw.data(), Ks, Ns, 1);
+  if (!rc && !w.ok) rc = fail("tensor-core weights could not be built");
+  if (!rc) rc = launch_row_exponents(re, A, K, zero, Ks, 1, (int)rows, st);
+  if (!rc) rc = launch_tc_linear(w, re, A, K, zero, Ks, C, N, zero, Ns, 1, (int)rows, false, st);
   cudaStreamSynchronize(st);
-  cudaFree(wt);
+  w.q.release();
+  w.fb.release();
+  re.buf.release();
   return rc;
+}
+
+// Host-only: the tensor-core weight packing of tc_gemm.cuh for one [K, N] block (tests/test_tc_pack_cpu.py).
+// q: 3*K*N uint16 (bf16 bits), laid out [n tile][K/32][slice][canonical NT x 32]; fb: N floats; *NT_out = tile width.
+int s7b_tc_pack_weights(const float* W, int32_t K, int32_t N, uint16_t* q, float* fb, int32_t* NT_out) {
+  if (!W || !q || !fb) return fail("null argument");
+  const int NT = tc_pick_nt(N);
+  if (K <= 0 || K % kTcKC != 0 || NT == 0) return fail("unsupported shape for the tensor-core linear");
+  tc_pack_block(W, K, N, NT, q, fb);
+  if (NT_out) *NT_out = NT;
+  return 0;
 }
 
 int s7b_engine_create(const S7bModelDesc* d, S7bEngine** out) {
@@ -589,8 +777,12 @@ void s7b_engine_destroy(S7bEngine* e) {
   if (e->g_out) cudaEventDestroy(e->g_out);
   e->d_nE.release();
   for (auto& kv : e->params) kv.second.release();
-  for (auto& L : e->layers)
+  for (auto& L : e->layers) {
     for (auto& kv : L.params) kv.second.release();
+    for (auto& kv : L.tcw)
+      if (kv.second) { kv.second->q.release(); kv.second->fb.release(); delete kv.second; }
+  }
+  for (RowExp* r : {&e->re_mid, &e->re_h, &e->re_dg, &e->re_dx}) r->buf.release();
   DevBuf* bufs[] = {&e->rec, &e->Y, &e->rlen, &e->emb, &e->dY_acc, &e->dEdr_acc, &e->demb_acc, &e->fedge,
                     &e->mid, &e->h, &e->dh, &e->dg, &e->dx, &e->dwbuf, &e->tmpA, &e->tmpB, &e->energy,
                     &e->atomic_energy, &e->forces, &e->virial, &e->atomic_virial, &e->hs_species, &e->hs_rowptr, &e->hs_src,
@@ -627,11 +819,21 @@ int s7b_engine_set_param(S7bEngine* e, const char* name, int layer, const float*
   if (dst->ensure(numel * sizeof(float))) return fail("cudaMalloc failed for parameter " + nm);
   S7B_CUDA_CHECK(cudaMemcpy(dst->p, host, numel * sizeof(float), cudaMemcpyHostToDevice));
   if (layer >= 0 && (nm == "si1" || nm == "si1T" || nm == "sc" || nm == "scT" || nm == "si2" || nm == "si2T")) {
-    DevBuf& hi = e->layers[layer].params[nm + ".hi"];
-    DevBuf& lo = e->layers[layer].params[nm + ".lo"];
-    if (hi.ensure(numel * sizeof(float)) || lo.ensure(numel * sizeof(float))) return fail("cudaMalloc failed for parameter " + nm);
-    split_tf32_kernel<<<256, 256>>>(dst->as<float>(), hi.as<float>(), lo.as<float>(), numel);
-    S7B_CUDA_CHECK(cudaDeviceSynchronize());
+    // tensor-core form: block shapes from the layer configuration
+    LayerCfg& L = e->layers[layer];
+    int Ks[kMaxL] = {0, 0, 0, 0}, Ns[kMaxL] = {0, 0, 0, 0}, n_l = 0;
+    const bool T = nm.back() == 'T';
+    if (nm.rfind("si1", 0) == 0) { n_l = L.n_lx; for (int l = 0; l < n_l; ++l) { Ks[l] = L.x_muls[l]; Ns[l] = L.x_muls[l]; } }
+    else if (nm.rfind("sc", 0) == 0) { n_l = std::min(L.n_lx, L.n_lg); for (int l = 0; l < n_l; ++l) { Ks[l] = L.x_muls[l]; Ns[l] = L.g_muls[l]; } }
+    else { n_l = L.n_lg; for (int l = 0; l < n_l; ++l) { Ks[l] = L.mid_K[l]; Ns[l] = L.g_muls[l]; } }
+    if (T) for (int l = 0; l < n_l; ++l) std::swap(Ks[l], Ns[l]);
+    size_t expect = 0;
+    for (int l = 0; l < n_l; ++l) expect += (size_t)Ks[l] * Ns[l];
+    if (expect != numel) return fail("parameter " + nm + ": size does not match the layer configuration");
+    TcWeights*& w = L.tcw[nm];
+    if (!w) w = new TcWeights();
+    if (tc_build_weights(*w, host, Ks, Ns, n_l)) return 1;
+    ++g_alloc_gen;
   }
   return 0;
 }
@@ -653,6 +855,7 @@ int s7b_engine_set_graph(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t
   if (n_edges >= ((int64_t)1 << 31)) return fail("more than 2^31-1 edges per GPU are not supported");
   e->n_nodes = n_nodes;
   e->n_local = n_local;
+  e->n_interior = n_local;
   e->n_edges = n_edges;
   e->d_species = d_species;
   e->d_rowptr = d_rowptr;
@@ -713,6 +916,13 @@ int s7b_engine_set_graph(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t
   rc |= e->forces.ensure(Nn * 3 * sizeof(float));
   if (e->want_atomic_virial) rc |= e->atomic_virial.ensure(Nn * 6 * sizeof(float));
   if (rc) return fail("cudaMalloc failed while sizing step buffers");
+  return 0;
+}
+
+int s7b_engine_set_interior(S7bEngine* e, int32_t n_interior) {
+  if (!e) return fail("null engine");
+  if (n_interior < 0 || n_interior > e->n_local) return fail("n_interior out of range");
+  e->n_interior = n_interior;
   return 0;
 }
 
@@ -793,11 +1003,14 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       return 0;
     }
     case S7B_STAGE_FWD_LAYER:
-    case S7B_STAGE_FWD_LAYER_A: {
+    case S7B_STAGE_FWD_LAYER_A:
+    case S7B_STAGE_FWD_CONV_INTERIOR:
+    case S7B_STAGE_FWD_LAYER_A2: {
       if (t < 0 || t >= T) return fail("layer out of range");
       const LayerCfg& L = e->layers[t];
       if (Nl == 0) return 0;
-      if (!table && E > 0) {
+      const bool head = stage != S7B_STAGE_FWD_LAYER_A2;
+      if (head && !table && E > 0) {
         // exact radial MLP (convolution.py:121): emb -> h1 -> h2 -> w
         const float *w0 = lparam(e, t, "mlp0"), *w1 = lparam(e, t, "mlp1"), *w2 = lparam(e, t, "mlp2");
         if (require(w0, "mlp0") || require(w1, "mlp1") || require(w2, "mlp2")) return 1;
@@ -806,11 +1019,13 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         if (dense_gemm(e->emb.as<float>(), nb, e->h1[t].as<float>(), h0, w0, E, kEpiSiluStoreZ, nullptr, e->z1[t].as<float>(), false, st)) return 1;
         if (dense_gemm(e->h1[t].as<float>(), h0, e->h2[t].as<float>(), h1, w1, E, kEpiSiluStoreZ, nullptr, e->z2[t].as<float>(), false, st)) return 1;
         if (dense_gemm(e->h2[t].as<float>(), h1, e->wbuf[t].as<float>(), L.W, w2, E, kEpiNone, nullptr, nullptr, false, st)) return 1;
-      } else if (table) {
+      } else if (head && table) {
         if (require(lparam(e, t, "table"), "table") || require(lparam(e, t, "table23"), "table23")) return 1;
       }
       // convolution: gather + tensor product + scatter (raw sums; 1/denominator is folded into si2)
       ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
+      if (stage == S7B_STAGE_FWD_CONV_INTERIOR) ca.n_dst = e->n_interior;
+      if (stage == S7B_STAGE_FWD_LAYER_A2) ca.n_begin = e->n_interior;
       {
         const bool par = e->concurrent && g_opt_concurrent && !e->prof.enabled && L.n_lx > 1;
         if (par) S7B_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
@@ -825,12 +1040,13 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
           }
         }
       }
+      if (stage == S7B_STAGE_FWD_CONV_INTERIOR) return 0;
       // self_interaction_2 accumulated onto the self-connection already stored in g[t]
       const float* si2 = lparam(e, t, "si2");
       if (require(si2, "si2")) return 1;
       {
         ProfScope ps(e->prof, st, "si2_gemm", t);
-        if (irreps_linear(e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st, lparam(e, t, "si2T.hi"), lparam(e, t, "si2T.lo"))) return 1;
+        if (node_linear(L, "si2", e->re_mid, true, L.n_lg, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st)) return 1;
       }
       // gate
       {
@@ -844,9 +1060,9 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         if (require(si1, "si1")) return 1;
         ProfScope ps(e->prof, st, "si1_gemm", t + 1);
         // self_interaction_1 of the next layer -> local rows of x[t+1] (ghost rows: caller's exchange)
-        if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st, lparam(e, t + 1, "si1T.hi"), lparam(e, t + 1, "si1T.lo"))) return 1;
+        if (node_linear(N, "si1", e->re_h, true, N.n_lx, e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st)) return 1;
       }
-      if (stage == S7B_STAGE_FWD_LAYER_A) return 0;
+      if (stage != S7B_STAGE_FWD_LAYER) return 0;
     }
     // fall through: FWD_LAYER = FWD_LAYER_A + FWD_LAYER_SC
     case S7B_STAGE_FWD_LAYER_SC: {
@@ -860,7 +1076,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       // exchange of x[t+1], so multi-GPU callers overlap the two
       S7B_CUDA_CHECK(cudaMemsetAsync(e->g[t + 1].p, 0, (size_t)Nl * N.dim_g * sizeof(float), st));
       const int n_sc = std::min(N.n_lx, N.n_lg);
-      if (irreps_linear(e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->g[t + 1].as<float>(), N.dim_g, N.g_off, N.g_muls, n_sc, sc, Nl, false, st, lparam(e, t + 1, "scT.hi"), lparam(e, t + 1, "scT.lo"))) return 1;
+      if (node_linear(N, "sc", e->re_h, false, N.n_lx, e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->g[t + 1].as<float>(), N.dim_g, N.g_off, N.g_muls, n_sc, sc, Nl, false, st)) return 1;
       return 0;
     }
     case S7B_STAGE_FWD_END: {
@@ -876,25 +1092,30 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       }
       return 0;
     }
-    case S7B_STAGE_BWD_LAYER_A: {
+    case S7B_STAGE_BWD_LAYER_A:
+    case S7B_STAGE_BWD_LAYER_A1:
+    case S7B_STAGE_BWD_LAYER_A2: {
       if (t < 0 || t >= T) return fail("layer out of range");
       const LayerCfg& L = e->layers[t];
-      if (t > 0 && Nn > 0) S7B_CUDA_CHECK(cudaMemsetAsync(e->dx.p, 0, (size_t)Nn * L.dim_x * sizeof(float), st));
+      const bool head = stage != S7B_STAGE_BWD_LAYER_A2, tail = stage != S7B_STAGE_BWD_LAYER_A1;
+      if (head && t > 0 && Nn > 0) S7B_CUDA_CHECK(cudaMemsetAsync(e->dx.p, 0, (size_t)Nn * L.dim_x * sizeof(float), st));
       if (Nl == 0) return 0;
-      {
-        ProfScope ps(e->prof, st, "gate_bwd", t);
-        gate_bwd_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl);
-        S7B_LAUNCH_CHECK();
-      }
-      const float* si2T = lparam(e, t, "si2T");
-      if (require(si2T, "si2T")) return 1;
-      // d(mid) = dg * si2^T
-      {
+      if (head) {
+        {
+          ProfScope ps(e->prof, st, "gate_bwd", t);
+          gate_bwd_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl);
+          S7B_LAUNCH_CHECK();
+        }
+        const float* si2T = lparam(e, t, "si2T");
+        if (require(si2T, "si2T")) return 1;
+        // d(mid) = dg * si2^T
         ProfScope ps(e->prof, st, "si2T_gemm", t);
-        if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st, lparam(e, t, "si2.hi"), lparam(e, t, "si2.lo"))) return 1;
+        if (node_linear(L, "si2T", e->re_dg, true, L.n_lg, e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st)) return 1;
       }
       if (E > 0) {
         ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
+        if (stage == S7B_STAGE_BWD_LAYER_A1) ca.n_begin = e->n_interior;     // boundary atoms first: they own the ghost rows of dx
+        if (stage == S7B_STAGE_BWD_LAYER_A2) ca.n_dst = e->n_interior;
         const bool par = e->concurrent && g_opt_concurrent && !e->prof.enabled && L.n_lx > 1;
         if (par) S7B_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
         for (int l1 = 0; l1 < L.n_lx; ++l1) {
@@ -909,7 +1130,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
             S7B_CUDA_CHECK(cudaStreamWaitEvent(st, e->ev_join[l1], 0));
           }
         }
-        if (!table) {
+        if (!table && tail) {
           // radial MLP backward: dw -> demb (accumulated over layers)
           const float *w0T = lparam(e, t, "mlp0T"), *w1T = lparam(e, t, "mlp1T"), *w2T = lparam(e, t, "mlp2T");
           if (require(w0T, "mlp0T") || require(w1T, "mlp1T") || require(w2T, "mlp2T")) return 1;
@@ -936,10 +1157,10 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       if (stage != S7B_STAGE_BWD_LAYER_B2) {
         const int n_sc = std::min(L.n_lx, L.n_lg);
         S7B_CUDA_CHECK(cudaMemsetAsync(e->dh.p, 0, (size_t)Nl * L.dim_x * sizeof(float), st));
-        if (irreps_linear(e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, n_sc, scT, Nl, false, st, lparam(e, t, "sc.hi"), lparam(e, t, "sc.lo"))) return 1;
+        if (node_linear(L, "scT", e->re_dg, false, L.n_lg, e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, n_sc, scT, Nl, false, st)) return 1;
       }
       if (stage != S7B_STAGE_BWD_LAYER_B1) {
-        if (irreps_linear(e->dx.as<float>(), L.dim_x, L.x_off, L.x_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, L.n_lx, si1T, Nl, true, st, lparam(e, t, "si1.hi"), lparam(e, t, "si1.lo"))) return 1;
+        if (node_linear(L, "si1T", e->re_dx, true, L.n_lx, e->dx.as<float>(), L.dim_x, L.x_off, L.x_muls, e->dh.as<float>(), L.dim_x, L.x_off, L.x_muls, L.n_lx, si1T, Nl, true, st)) return 1;
       }
       return 0;
     }
@@ -1003,7 +1224,7 @@ int s7b_engine_compute(S7bEngine* e, void* stream) {
   const std::vector<int64_t> key = {
       e->n_nodes, e->n_local, e->E_cap, e->n_edges > 0 ? 1 : 0, (int64_t)(uintptr_t)e->d_species,
       (int64_t)(uintptr_t)e->d_rowptr, (int64_t)(uintptr_t)e->d_src, (int64_t)(uintptr_t)e->d_edge_vec,
-      g_alloc_gen, g_opt_concurrent, g_opt_tc_gemm, e->concurrent ? 1 : 0};
+      g_alloc_gen, g_opt_concurrent, g_opt_tc_gemm + 2 * g_opt_tc_swizzle, e->concurrent ? 1 : 0};
   if (!e->gexec || key != e->g_key) {
     if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
     const int64_t before = g_launches + g_conv_launches;

@@ -232,6 +232,44 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const int* _
   }
 }
 
+// Ghost-exchange pack / unpack (multi-GPU; replaces pair_e3gnn_parallel.cpp:698-799's pack/unpack of
+// x_ghost / dE_dx rows): out[i, :] = src[idx[i], :]  and  dst[idx[i], :] += in[i, :].  One thread per
+// float4 (VEC) or float of a row; indices of one scatter call are unique, so the add is a plain
+// read-modify-write and the summation order over peers (one call per peer) is deterministic.
+template <bool VEC>
+__global__ void gather_rows_idx_kernel(const float* __restrict__ src, int ld_src, const int* __restrict__ idx,
+                                       long long n, int width, float* __restrict__ out) {
+  const int w = VEC ? width >> 2 : width;
+  const long long total = n * w;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / w;
+    const int c = (int)(t - i * w);
+    const float* row = src + (size_t)__ldg(idx + i) * ld_src;
+    if (VEC) reinterpret_cast<float4*>(out)[t] = __ldg(reinterpret_cast<const float4*>(row) + c);
+    else out[t] = __ldg(row + c);
+  }
+}
+template <bool VEC>
+__global__ void scatter_add_rows_idx_kernel(float* __restrict__ dst, int ld_dst, const int* __restrict__ idx,
+                                            long long n, int width, const float* __restrict__ in) {
+  const int w = VEC ? width >> 2 : width;
+  const long long total = n * w;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / w;
+    const int c = (int)(t - i * w);
+    float* row = dst + (size_t)__ldg(idx + i) * ld_dst;
+    if (VEC) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(in) + t);
+      float4* p = reinterpret_cast<float4*>(row) + c;
+      float4 o = *p;
+      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      *p = o;
+    } else {
+      row[c] += __ldg(in + t);
+    }
+  }
+}
+
 // Readout (two bias-free linears folded into one vector wr), species-wise rescale, energy sum and
 // the seed of the backward pass dE/dh = scale[s] * wr.  One warp per atom.
 __global__ void readout_kernel(const float* __restrict__ h, const float* __restrict__ wr,

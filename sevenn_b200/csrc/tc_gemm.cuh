@@ -1,28 +1,53 @@
-// Block-diagonal irreps linear on the 5th-generation tensor cores (tcgen05, sm_100a):
-//   C[(n,i), :N] (+)= A[(n,i), :K] * W[K, N]        fp32 in / fp32 out, 3xTF32 inside
+// Block-diagonal irreps linear on the 5th-generation tensor cores (tcgen05 + TMEM + TMA, sm_100a):
+//   C[(n,i), :N] (+)= A[(n,i), :K] * W[K, N]        fp32 in / fp32 out
 // Same operand addressing as blocklin_gemm_kernel (node_kernels.cuh); replaces e3nn o3.Linear
-// (sevenn/nn/linear.py:94-100) for self_interaction_1/2 and the self connection.
+// (sevenn/nn/linear.py:94-100) for self_interaction_1/2 and the self connection, forward and backward.
 //
-// Precision: every fp32 operand is split a = a_hi + a_lo with a_hi = rna_tf32(a) and
-// a_lo = rna_tf32(a - a_hi) (round-to-nearest, so the hardware's truncation to TF32 loses nothing and
-// the residual 2^-23-level errors are unbiased); the tensor core accumulates all four products
-// a_hi*b_hi + a_lo*b_hi + a_hi*b_lo + a_lo*b_lo in fp32 in TMEM.  Weights are pre-split once.
+// Arithmetic: error-free tensor-core accumulation.  The tensor core adds into its fp32 accumulator with
+// truncation, which biases long fp32/TF32 accumulations (round 1 measured -8.7e-6 eV/atom with 3xTF32).
+// Here every operand is first brought to 24-bit fixed point relative to a power-of-two bound of its row
+// (A: per (node, component) row over all K, from row_exponent_kernel; W: per output column, on the host)
+// and cut into three signed 8-bit slices  q = q0*2^16 + q1*2^8 + q2,  |q_i| <= 128, each exactly
+// representable in bf16.  Then
+//     a*b*2^-(Ea+Eb-14) = (A0+A1+A2)(B0+B1+B2),   A0 = q0, A1 = q1*2^-8, A2 = q2*2^-16 (same for B)
+//   ACC0 = sum_k A0*B0                 integers < 2^23: EXACT in the fp32 accumulator, nothing to truncate
+//   ACC1 = sum_k A0*B1+A1*B0+A0*B2+A1*B1+A2*B0     2^-8 of ACC0: its truncation is 2^-32 relative
+//   C    = 2^(Ea-7) * 2^(Eb-7) * (ACC0 + ACC1)     one round-to-nearest fp32 add in the epilogue
+// (the dropped A1*B2, A2*B1, A2*B2 are < 2^-24 relative).  Six kind::f16 (bf16) MMAs per K = 16 step cost
+// the same tensor time as 3xTF32.  Emulated bit for bit on the CPU by tests/test_tc_pack_cpu.py.
 //
-// Structure (one CTA = 128 threads = one 128-row tile x one N chunk of <= 256 columns):
-//   * all threads stage a [128 x 32] A chunk (split hi/lo on the fly) and the matching
-//     [N x 32] W^T chunk into shared memory in the canonical K-major, no-swizzle UMMA layout
-//     (8-row x 16-byte core matrices; LBO = 128 B along K, SBO = 1024 B between row groups);
-//   * one elected thread issues 16 tcgen05.mma.kind::tf32 (M=128, N, K=8) per chunk and commits to an
-//     mbarrier; two stages, so the loads of chunk c+1 overlap the MMAs of chunk c;
-//   * the accumulator [128 x N] fp32 lives in TMEM; after the last commit each warp reads its 32
-//     lanes with tcgen05.ld.32x32b.x32 and writes the rows out (optionally C += ...).
+// Structure (persistent, one CTA per SM, 320 threads, tiles of 128 rows x NT <= 128 columns):
+//   warp 8   TMA producer: per 32-wide K chunk one cp.async.bulk.tensor (3-D map over (k, component,
+//            node); 128B swizzle) for the raw fp32 A tile and one cp.async.bulk for the pre-sliced,
+//            pre-arranged W chunk, both completing on the stage's mbarrier (3-stage ring)
+//   warps 0-3 transform: thread r converts row r of the raw tile into the three bf16 slices, written in
+//            the canonical K-major UMMA layout (8-row x 16-byte core matrices)
+//   warp 9   MMA issuer: one thread issues 12 tcgen05.mma per chunk (M = 128, N = NT, K = 16) into the
+//            two TMEM accumulators of the tile; tcgen05.commit frees the stage / publishes the tile
+//   warps 4-7 epilogue: tcgen05.ld the accumulators (double-buffered in TMEM, so the next tile's MMAs
+//            overlap), scale, transpose a 32x32 slab through shared memory and write/accumulate C with
+//            128-byte coalesced row segments.
 #pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "node_kernels.cuh"
 
 namespace s7b {
 
-constexpr int kTcBM = 128, kTcKC = 32, kTcThreads = 128, kTcMaxN = 256;
+constexpr int kTcBM = 128;          // rows (nodes) per tile
+constexpr int kTcKC = 32;           // K elements per pipeline stage
+constexpr int kTcMaxNT = 128;       // columns per tile (two accumulators x two buffers = 512 TMEM columns)
+constexpr int kTcStages = 3;
+constexpr int kTcThreads = 320;
+constexpr int kTcRawBytes = kTcBM * kTcKC * 4;            // 16 KB raw fp32 A chunk
+constexpr int kTcASliceBytes = kTcBM * kTcKC * 2;         // 8 KB per bf16 slice
+constexpr int kTcBSliceBytes = kTcMaxNT * kTcKC * 2;      // 8 KB per bf16 slice (NT = 128)
+constexpr int kTcStageBytes = kTcRawBytes + 3 * kTcASliceBytes + 3 * kTcBSliceBytes;   // 64 KB
+constexpr int kTcEpiBytes = 4 * 32 * 33 * 4;              // per-warp 32 x 33 transpose scratch
+constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + kTcEpiBytes + 1024 /*alignment slack*/;
+constexpr int kTcZeroRow = -1000;   // row exponent of an all-zero row
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -41,11 +66,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
+// TMA: 3-D tiled tensor load (coordinates innermost first) completing on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+// TMA engine, linear form: contiguous global -> shared bulk copy completing on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// lbo = byte distance of core matrices adjacent in K, sbo = of 8-row groups adjacent in M/N.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -54,17 +101,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;     // descriptor version for sm_100
   return d;                   // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE
 }
-// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128.
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -80,163 +127,287 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 2^e as a float (e clamped to the normal range)
+__device__ __forceinline__ float exp2i(int e) {
+  e = e < -126 ? -126 : (e > 127 ? 127 : e);
+  return __int_as_float((e + 127) << 23);
 }
 
-// round-to-nearest conversion to a TF32-representable fp32 value (the tensor core itself would truncate)
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
+// ---- row exponents --------------------------------------------------------------------------------
+// E(n, i) with max_k |A[(n,i), k]| < 2^E  (kTcZeroRow for an all-zero / denormal row); one warp per row.
+struct RowExpArgs {
+  const float* A;
+  int* E;                 // [n_nodes, rows_per_node]
+  int lda, n_nodes, rows_per_node, nblocks;
+  int d[kMaxL], K[kMaxL], a_off[kMaxL], row_base[kMaxL];
+};
+
+__global__ void row_exponent_kernel(const RowExpArgs a) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)a.n_nodes * a.rows_per_node;
+  for (long long w = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < total;
+       w += (long long)gridDim.x * warps_per_block) {
+    const int n = (int)(w / a.rows_per_node);
+    const int rr = (int)(w - (long long)n * a.rows_per_node);
+    int b = 0;
+    while (b + 1 < a.nblocks && rr >= a.row_base[b + 1]) ++b;
+    const int i = rr - a.row_base[b];
+    const float4* row = reinterpret_cast<const float4*>(a.A + (size_t)n * a.lda + a.a_off[b] + (size_t)i * a.K[b]);
+    uint32_t m = 0;
+    for (int q = lane; q < (a.K[b] >> 2); q += 32) {
+      const float4 v = __ldg(row + q);
+      m = max(m, __float_as_uint(v.x) & 0x7fffffffu);
+      m = max(m, __float_as_uint(v.y) & 0x7fffffffu);
+      m = max(m, __float_as_uint(v.z) & 0x7fffffffu);
+      m = max(m, __float_as_uint(v.w) & 0x7fffffffu);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) {
+      const int ex = (int)(m >> 23);
+      a.E[w] = (ex == 0 || ex == 255) ? kTcZeroRow : ex - 126;     // |a| < 2^(ex-126)
+    }
+  }
 }
 
-// canonical K-major no-swizzle offset (bytes) of the 16-byte chunk (row r, k-quad q) in a [rows x 32] tile
-__device__ __forceinline__ uint32_t canon_off(int r, int q) { return (uint32_t)((r & 7) * 16 + (r >> 3) * 1024 + q * 128); }
-
+// ---- the GEMM --------------------------------------------------------------------------------------
 struct TcLinBlock {
-  const float* Wt_hi;   // [N, K] row-major (= W^T), truncated to TF32
-  const float* Wt_lo;   // [N, K] remainder
-  int d, K, N;
-  int a_off, a_cs, c_off, c_cs;
+  const uint16_t* Wq;   // pre-sliced weights: [n_ntiles][K/32][3 slices][canonical NT x 32 bf16]
+  const float* fb;      // [N] column scales 2^(Eb-7)
+  int d, K, N, NT;
+  int c_off, c_cs;
+  int row_base;         // first row of this block in the row-exponent array
+  int tile0;            // index of the block's first tile; tiles ordered [node tile][component][n tile]
 };
 struct TcLinArgs {
-  const float* A;
   float* C;
-  int lda, ldc, n_nodes, accumulate, nblocks;
+  const int* E;         // row exponents of A, [n_nodes, rows_per_node]
+  int ldc, n_nodes, rows_per_node, accumulate, nblocks, n_tiles, swizzle;
   TcLinBlock blk[kMaxL];
 };
+struct TcMaps { CUtensorMap m[kMaxL]; };   // per block: A viewed as (k, component, node), fp32
 
-// dynamic smem: 2 stages x (A_hi 16K + A_lo 16K + B_hi nb*128 + B_lo nb*128) ; grid = (row tiles, N chunks, blocks)
-__global__ void __launch_bounds__(kTcThreads, 1) blocklin_tc_kernel(const TcLinArgs a, int n_chunk) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t mma_done[2];
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar_full_raw[kTcStages], bar_full_ops[kTcStages], bar_empty[kTcStages];
+  __shared__ uint64_t bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_sh;
 
-  const TcLinBlock b = a.blk[blockIdx.z];
-  const int rows = a.n_nodes * b.d;
-  const int row0 = blockIdx.x * kTcBM;
-  const int col0 = blockIdx.y * n_chunk;
-  if (row0 >= rows || col0 >= b.N) return;        // uniform per CTA
-  const int nb = min(n_chunk, b.N - col0);         // columns of this CTA (multiple of 16)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  const uint32_t stage_bytes = 2u * 16384u + 2u * (uint32_t)n_chunk * 128u;
-  uint8_t* stage_ptr[2] = {smem, smem + stage_bytes};
-
-  // TMEM columns: power of two >= 32 covering nb
-  uint32_t ncols = 32;
-  while ((int)ncols < nb) ncols <<= 1;
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(ncols) : "memory");
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(&mma_done[0], 1);
-    mbar_init(&mma_done[1], 1);
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(&bar_full_raw[s], 1);
+      mbar_init(&bar_full_ops[s], 128);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_acc_full[b], 1);
+      mbar_init(&bar_acc_empty[b], 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = tmem_base_sh;
+  const uint32_t tmem_base = tmem_base_sh;
 
-  // A row of this thread
-  const int gr = row0 + tid;
-  const float* a_row = nullptr;
-  if (gr < rows) {
-    const int n = gr / b.d, i = gr - n * b.d;
-    a_row = a.A + (size_t)n * a.lda + b.a_off + i * b.a_cs;
-  }
-  const uint32_t idesc = umma_idesc_tf32(nb);
-  const int n_kc = b.K / kTcKC;
+  // tile t -> (block, node tile, component, n tile)
+  auto decode = [&](int t, int& b, int& mt, int& ci, int& nt) {
+    b = 0;
+    while (b + 1 < a.nblocks && t >= a.blk[b + 1].tile0) ++b;
+    const int rel = t - a.blk[b].tile0;
+    const int nnt = a.blk[b].N / a.blk[b].NT;
+    nt = rel % nnt;
+    const int r2 = rel / nnt;
+    ci = r2 % a.blk[b].d;
+    mt = r2 / a.blk[b].d;
+  };
 
-  for (int kc = 0; kc < n_kc; ++kc) {
-    const int s = kc & 1;
-    if (kc >= 2) mbar_wait(&mma_done[s], (uint32_t)(((kc >> 1) - 1) & 1));   // stage free again
-    uint8_t* sA_hi = stage_ptr[s];
-    uint8_t* sA_lo = sA_hi + 16384;
-    uint8_t* sB_hi = sA_lo + 16384;
-    uint8_t* sB_lo = sB_hi + (size_t)n_chunk * 128;
-    // ---- A chunk: row tid, k = kc*32 .. +31, split hi / lo
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a_row != nullptr) v = __ldg(reinterpret_cast<const float4*>(a_row + kc * kTcKC + 4 * q));
-      float4 h, l;
-      h.x = rna_tf32(v.x); l.x = rna_tf32(v.x - h.x);
-      h.y = rna_tf32(v.y); l.y = rna_tf32(v.y - h.y);
-      h.z = rna_tf32(v.z); l.z = rna_tf32(v.z - h.z);
-      h.w = rna_tf32(v.w); l.w = rna_tf32(v.w - h.w);
-      const uint32_t off = canon_off(tid, q);
-      *reinterpret_cast<float4*>(sA_hi + off) = h;
-      *reinterpret_cast<float4*>(sA_lo + off) = l;
-    }
-    // ---- W^T chunk: rows col0 .. col0+nb-1
-    for (int r = tid; r < nb; r += kTcThreads) {
-      const float* wh = b.Wt_hi + (size_t)(col0 + r) * b.K + kc * kTcKC;
-      const float* wl = b.Wt_lo + (size_t)(col0 + r) * b.K + kc * kTcKC;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const uint32_t off = canon_off(r, q);
-        *reinterpret_cast<float4*>(sB_hi + off) = __ldg(reinterpret_cast<const float4*>(wh + 4 * q));
-        *reinterpret_cast<float4*>(sB_lo + off) = __ldg(reinterpret_cast<const float4*>(wl + 4 * q));
-      }
-    }
-    fence_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t aH = smem_u32(sA_hi), aL = smem_u32(sA_lo), bH = smem_u32(sB_hi), bL = smem_u32(sB_lo);
-#pragma unroll
-      for (int j = 0; j < kTcKC / 8; ++j) {
-        const uint32_t ko = (uint32_t)j * 256u;   // two 16-byte K chunks per MMA
-        const uint64_t dAh = umma_desc(aH + ko, 128, 1024), dAl = umma_desc(aL + ko, 128, 1024);
-        const uint64_t dBh = umma_desc(bH + ko, 128, 1024), dBl = umma_desc(bL + ko, 128, 1024);
-        umma_tf32(tmem_d, dAh, dBh, idesc, (kc > 0 || j > 0) ? 1u : 0u);
-        umma_tf32(tmem_d, dAl, dBh, idesc, 1u);
-        umma_tf32(tmem_d, dAh, dBl, idesc, 1u);
-        umma_tf32(tmem_d, dAl, dBl, idesc, 1u);
-      }
-      umma_commit(&mma_done[s]);
-    }
-  }
-  // ---- wait for the last commit (covers every MMA issued before it)
-  {
-    const int last = n_kc - 1;
-    mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1));
-  }
-  tc_fence_after();
-
-  // ---- epilogue: warp w owns TMEM lanes 32w .. 32w+31 == rows row0 + 32w + lane
-  const int r = row0 + warp * 32 + lane;
-  float* c_row = nullptr;
-  if (r < rows) {
-    const int n = r / b.d, ii = r - n * b.d;
-    c_row = a.C + (size_t)n * a.ldc + b.c_off + ii * b.c_cs + col0;
-  }
-  for (int c = 0; c < nb; c += 32) {
-    uint32_t v[32];
-    tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-    if (c_row != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (c + j < nb) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          float4* p = reinterpret_cast<float4*>(c_row + c + j);
-          if (a.accumulate) {
-            const float4 old = *p;
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          *p = o;
+  if (warp == 8) {
+    // =================== TMA producer ===================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        int b, mt, ci, nt;
+        decode(t, b, mt, ci, nt);
+        const TcLinBlock& B = a.blk[b];
+        const int n_kc = B.K / kTcKC;
+        const uint32_t b_bytes = 3u * (uint32_t)B.NT * kTcKC * 2u;
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(B.Wq) + (size_t)nt * n_kc * b_bytes;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int s = it % kTcStages;
+          mbar_wait(&bar_empty[s], ((it / kTcStages) & 1) ^ 1);
+          uint8_t* st = smem + (size_t)s * kTcStageBytes;
+          mbar_expect_tx(&bar_full_raw[s], (uint32_t)kTcRawBytes + b_bytes);
+          tma_load_3d(st, &maps.m[b], kc * kTcKC, ci, mt * kTcBM, &bar_full_raw[s]);
+          bulk_load(st + kTcRawBytes + 3 * kTcASliceBytes, wsrc + (size_t)kc * b_bytes, b_bytes, &bar_full_raw[s]);
         }
       }
     }
+  } else if (warp < 4) {
+    // =================== transform: raw fp32 row -> three bf16 slices ===================
+    const int r = tid;                                  // row of the tile
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+      int b, mt, ci, nt;
+      decode(t, b, mt, ci, nt);
+      const TcLinBlock& B = a.blk[b];
+      const int n_kc = B.K / kTcKC;
+      const int node = mt * kTcBM + r;
+      int Ea = kTcZeroRow;
+      if (node < a.n_nodes) Ea = __ldg(a.E + (size_t)node * a.rows_per_node + B.row_base + ci);
+      const float sc = (Ea == kTcZeroRow) ? 0.0f : exp2i(23 - Ea);     // t = a * sc, |t| < 2^23
+      const float M = 12582912.0f;                                      // 1.5 * 2^23: (x + M) - M = rint(x)
+      const uint32_t swz = a.swizzle ? (uint32_t)(r & 7) : 0u;
+      for (int kc = 0; kc < n_kc; ++kc, ++it) {
+        const int s = it % kTcStages;
+        mbar_wait(&bar_full_raw[s], (it / kTcStages) & 1);
+        uint8_t* st = smem + (size_t)s * kTcStageBytes;
+        const uint8_t* raw = st + (size_t)r * 128;
+        uint8_t* a0 = st + kTcRawBytes;
+        uint8_t* a1 = a0 + kTcASliceBytes;
+        uint8_t* a2 = a1 + kTcASliceBytes;
+        const uint32_t row_off = (uint32_t)((r & 7) * 16 + (r >> 3) * 512);
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {                // 8 consecutive k = one 16-byte core-matrix row
+          const float4 v0 = *reinterpret_cast<const float4*>(raw + (((uint32_t)(2 * kq) ^ swz) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(raw + (((uint32_t)(2 * kq + 1) ^ swz) << 4));
+          const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          float s0[8], s1[8], s2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float tt = x[j] * sc;
+            const float q0 = __fadd_rn(__fmaf_rn(tt, 1.52587890625e-05f, M), -M);        // rint(t / 2^16)
+            const float r1 = __fmaf_rn(q0, -65536.0f, tt);                               // exact
+            const float q1 = __fadd_rn(__fmaf_rn(r1, 0.00390625f, M), -M);               // rint(r1 / 2^8)
+            const float r2 = __fmaf_rn(q1, -256.0f, r1);                                 // exact
+            const float q2 = __fadd_rn(__fadd_rn(r2, M), -M);                            // rint(r2)
+            s0[j] = q0;
+            s1[j] = q1 * 0.00390625f;
+            s2[j] = q2 * 1.52587890625e-05f;
+          }
+          const uint32_t off = row_off + (uint32_t)kq * 128u;
+          *reinterpret_cast<uint4*>(a0 + off) = make_uint4(pack_bf16(s0[0], s0[1]), pack_bf16(s0[2], s0[3]), pack_bf16(s0[4], s0[5]), pack_bf16(s0[6], s0[7]));
+          *reinterpret_cast<uint4*>(a1 + off) = make_uint4(pack_bf16(s1[0], s1[1]), pack_bf16(s1[2], s1[3]), pack_bf16(s1[4], s1[5]), pack_bf16(s1[6], s1[7]));
+          *reinterpret_cast<uint4*>(a2 + off) = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
+        }
+        fence_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        mbar_arrive(&bar_full_ops[s]);
+      }
+    }
+  } else if (warp == 9) {
+    // =================== MMA issuer ===================
+    if (lane == 0) {
+      uint32_t it = 0, tile_it = 0;
+      for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tile_it) {
+        int b, mt, ci, nt;
+        decode(t, b, mt, ci, nt);
+        const TcLinBlock& B = a.blk[b];
+        const int n_kc = B.K / kTcKC;
+        const int buf = tile_it & 1;
+        mbar_wait(&bar_acc_empty[buf], ((tile_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 * B.NT);
+        const uint32_t acc1 = acc0 + (uint32_t)B.NT;
+        const uint32_t idesc = umma_idesc_bf16(B.NT);
+        const uint32_t b_slice = (uint32_t)B.NT * kTcKC * 2u;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int s = it % kTcStages;
+          mbar_wait(&bar_full_ops[s], (it / kTcStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * kTcStageBytes + kTcRawBytes);
+          const uint32_t sb = sa + 3u * kTcASliceBytes;
+#pragma unroll
+          for (int j = 0; j < kTcKC / 16; ++j) {
+            const uint32_t ko = (uint32_t)j * 256u;     // two 16-byte K core matrices per MMA
+            const uint64_t dA0 = umma_desc(sa + ko, 128, 512);
+            const uint64_t dA1 = umma_desc(sa + kTcASliceBytes + ko, 128, 512);
+            const uint64_t dA2 = umma_desc(sa + 2 * kTcASliceBytes + ko, 128, 512);
+            const uint64_t dB0 = umma_desc(sb + ko, 128, 512);
+            const uint64_t dB1 = umma_desc(sb + b_slice + ko, 128, 512);
+            const uint64_t dB2 = umma_desc(sb + 2 * b_slice + ko, 128, 512);
+            const uint32_t first = (kc > 0 || j > 0) ? 1u : 0u;
+            umma_bf16(acc0, dA0, dB0, idesc, first);
+            umma_bf16(acc1, dA0, dB1, idesc, first);
+            umma_bf16(acc1, dA1, dB0, idesc, 1u);
+            umma_bf16(acc1, dA0, dB2, idesc, 1u);
+            umma_bf16(acc1, dA1, dB1, idesc, 1u);
+            umma_bf16(acc1, dA2, dB0, idesc, 1u);
+          }
+          umma_commit(&bar_empty[s]);                    // stage reusable once these MMAs have read it
+        }
+        umma_commit(&bar_acc_full[buf]);                 // accumulators of this tile complete
+      }
+    }
+  } else {
+    // =================== epilogue (warps 4..7 <-> TMEM lanes 32*(warp-4) ..) ===================
+    const int ew = warp - 4;
+    float* scratch = reinterpret_cast<float*>(smem + (size_t)kTcStages * kTcStageBytes) + ew * (32 * 33);
+    uint32_t tile_it = 0;
+    for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tile_it) {
+      int b, mt, ci, nt;
+      decode(t, b, mt, ci, nt);
+      const TcLinBlock& B = a.blk[b];
+      const int buf = tile_it & 1;
+      const int node_mine = mt * kTcBM + ew * 32 + lane;          // the row this thread holds in TMEM
+      int Ea = kTcZeroRow;
+      if (node_mine < a.n_nodes) Ea = __ldg(a.E + (size_t)node_mine * a.rows_per_node + B.row_base + ci);
+      const float fa = (Ea == kTcZeroRow) ? 0.0f : exp2i(Ea - 7);
+      mbar_wait(&bar_acc_full[buf], (tile_it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 2 * B.NT);
+      const int col0 = nt * B.NT;
+      for (int c = 0; c < B.NT; c += 32) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(lane_base + (uint32_t)c, v0);
+        tmem_ld32(lane_base + (uint32_t)(B.NT + c), v1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          scratch[lane * 33 + j] = (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * fa;
+        __syncwarp();
+        const int cc = c + lane;                                    // this lane's column of the slab
+        const bool col_ok = cc < B.NT;
+        const float fb = col_ok ? __ldg(B.fb + col0 + cc) : 0.0f;
+        const int node0 = mt * kTcBM + ew * 32;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int node = node0 + rr;
+          if (node >= a.n_nodes) break;                             // uniform over the warp
+          if (col_ok) {
+            float* p = a.C + (size_t)node * a.ldc + B.c_off + (size_t)ci * B.c_cs + col0 + cc;
+            float v = scratch[rr * 33 + lane] * fb;
+            if (a.accumulate) v += *p;
+            *p = v;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_acc_empty[buf]);
+    }
   }
+
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(ncols) : "memory");
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 

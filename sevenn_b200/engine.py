@@ -29,7 +29,8 @@ _lib = None
 
 S7B_MAX_LAYERS, S7B_MAX_L = 8, 4
 (STAGE_FWD_BEGIN, STAGE_FWD_LAYER, STAGE_FWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B,
- STAGE_BWD_END, STAGE_FWD_LAYER_A, STAGE_FWD_LAYER_SC, STAGE_BWD_LAYER_B1, STAGE_BWD_LAYER_B2) = range(10)
+ STAGE_BWD_END, STAGE_FWD_LAYER_A, STAGE_FWD_LAYER_SC, STAGE_BWD_LAYER_B1, STAGE_BWD_LAYER_B2,
+ STAGE_FWD_CONV_INTERIOR, STAGE_FWD_LAYER_A2, STAGE_BWD_LAYER_A1, STAGE_BWD_LAYER_A2) = range(14)
 
 
 class S7bModelDesc(ctypes.Structure):
@@ -47,7 +48,8 @@ class S7bModelDesc(ctypes.Structure):
 
 EXPORTS = [
     's7b_last_error', 's7b_version', 's7b_set_option', 's7b_dense_linear', 's7b_engine_create', 's7b_engine_destroy',
-    's7b_engine_set_atomic_virial',
+    's7b_engine_set_atomic_virial', 's7b_tc_pack_weights', 's7b_gather_rows', 's7b_scatter_add_rows',
+    's7b_engine_set_interior',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
     's7b_engine_buffer', 's7b_engine_compute_host', 's7b_engine_set_positions_host',
     's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_graph_stats', 's7b_engine_set_profiling',
@@ -74,6 +76,10 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_engine_destroy.argtypes = [vp]
     lib.s7b_engine_destroy.restype = None
     lib.s7b_engine_set_atomic_virial.argtypes = [vp, ctypes.c_int]
+    lib.s7b_tc_pack_weights.argtypes = [vp, i32, i32, vp, vp, ctypes.POINTER(i32)]
+    lib.s7b_gather_rows.argtypes = [vp, i32, vp, i64, i32, vp, vp]
+    lib.s7b_scatter_add_rows.argtypes = [vp, i32, vp, i64, i32, vp, vp]
+    lib.s7b_engine_set_interior.argtypes = [vp, i32]
     lib.s7b_engine_set_param.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, vp, sz]
     lib.s7b_engine_set_graph.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp]
     lib.s7b_engine_run_stage.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
@@ -348,6 +354,27 @@ class B200Engine:
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_interior(self, n_interior: int):
+        """owned atoms [0, n_interior) have no ghost neighbour (split stages of the multi-GPU runner)"""
+        check(self.lib.s7b_engine_set_interior(self._h, int(n_interior)))
+
+    # ---- ghost-exchange pack / unpack kernels (C ABI s7b_gather_rows / s7b_scatter_add_rows) ----------
+    def gather_rows(self, src, idx32, out):
+        """out[i] = src[idx32[i]] (rows of a 2-D float32 tensor; idx32 int32 on the device)"""
+        n = int(idx32.shape[0])
+        if n:
+            check(self.lib.s7b_gather_rows(src.data_ptr(), src.stride(0), idx32.data_ptr(), n, src.shape[1],
+                                           out.data_ptr(), self._stream()))
+        return out
+
+    def scatter_add_rows(self, dst, idx32, rows):
+        """dst[idx32[i]] += rows[i]; idx32 must hold unique indices"""
+        n = int(idx32.shape[0])
+        if n:
+            check(self.lib.s7b_scatter_add_rows(dst.data_ptr(), dst.stride(0), idx32.data_ptr(), n, dst.shape[1],
+                                                rows.data_ptr(), self._stream()))
+        return dst
 
     # ---- execution --------------------------------------------------------------------------------
     def run_stage(self, stage: int, layer: int = 0):

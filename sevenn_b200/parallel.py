@@ -14,8 +14,15 @@ between.  Here:
   share ONE ghost row (features are translation invariant), images of owned atoms need no ghost;
 * ghost rows are ordered by owner rank, so a forward exchange receives straight into the ghost
   rows of the engine's ``x`` buffer (zero-copy unpack) and a reverse exchange sends straight out of
-  the ghost rows of ``dx`` (zero-copy pack); all peers are served by ONE grouped
-  ``batch_isend_irecv`` (ncclGroupStart/End) per exchange instead of six ordered swaps;
+  the ghost rows of ``dx`` (zero-copy pack); all peers are served by ONE ``all_to_all_single`` with
+  uneven splits (grouped ncclSend/ncclRecv) per exchange instead of six ordered swaps; the other side
+  is packed / unpacked by the library's own kernels (``s7b_gather_rows`` / ``s7b_scatter_add_rows``);
+* owned atoms are ordered interior first (no ghost neighbour), boundary last, and every convolution is
+  split at that point: the interior part of layer t runs while the ghost rows of x(t) are still in
+  flight, and in the backward the boundary part runs first so that the ghost rows of dx(t) travel
+  while the interior part is computed (stages 10-13 of ``include/sevenn_b200.h``);
+* on CUDA the whole step -- kernels, pack/unpack and the NCCL calls -- is captured once into a CUDA
+  graph and replayed (``cuda_graph``), so the per-step host cost is one graph launch;
 * layer 0 needs no exchange: ghost species are known locally, so the first-layer features of
   ghosts are recomputed (the reference's trick, ``sevenn/model_build.py:383-421``);
 * energy = one scalar all-reduce; ghost forces = one more reverse (sum) exchange of [n_ghost, 3]
@@ -27,9 +34,9 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from .engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B, STAGE_BWD_LAYER_B1,
-                     STAGE_BWD_LAYER_B2, STAGE_FWD_BEGIN, STAGE_FWD_END, STAGE_FWD_LAYER,
-                     STAGE_FWD_LAYER_A, STAGE_FWD_LAYER_SC)
+from .engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_A1, STAGE_BWD_LAYER_A2, STAGE_BWD_LAYER_B,
+                     STAGE_BWD_LAYER_B1, STAGE_BWD_LAYER_B2, STAGE_FWD_BEGIN, STAGE_FWD_CONV_INTERIOR, STAGE_FWD_END,
+                     STAGE_FWD_LAYER, STAGE_FWD_LAYER_A, STAGE_FWD_LAYER_A2, STAGE_FWD_LAYER_SC)
 
 
 def owner_of(frac: np.ndarray, grid: Sequence[int]) -> np.ndarray:
@@ -45,7 +52,7 @@ def brick_decompose(pos: np.ndarray, cell: np.ndarray, species: np.ndarray, grid
     Returns a dict with
       global_ids [n_nodes]      global index of every local row (owned first, then ghosts)
       species    [n_nodes]
-      n_local, n_nodes
+      n_local, n_nodes, n_interior   owned atoms [0, n_interior) have no ghost neighbour
       edge_index [2, E]         local indices; [0] = owned centre (sorted), [1] = owned or ghost
       edge_vec   [E, 3]
       ghost_owner [n_ghost]     owning rank of each ghost row (non-decreasing)
@@ -67,6 +74,11 @@ def brick_decompose(pos: np.ndarray, cell: np.ndarray, species: np.ndarray, grid
         ei, ev, _ = neighbor_list_brute(pos, cell, True, cutoff)
     keep = owner[ei[0]] == rank
     ei, ev = ei[:, keep], ev[keep]
+    # owned atoms: interior (no remote neighbour) first, boundary last; global order within each class
+    is_boundary = np.zeros(len(pos), dtype=bool)
+    is_boundary[ei[0][owner[ei[1]] != rank]] = True
+    mine = np.concatenate([mine[~is_boundary[mine]], mine[is_boundary[mine]]])
+    n_interior = int((~is_boundary[mine]).sum())
     remote = np.unique(ei[1][owner[ei[1]] != rank])
     order = np.lexsort((remote, owner[remote]))            # by owner, then global id
     ghosts = remote[order]
@@ -77,7 +89,7 @@ def brick_decompose(pos: np.ndarray, cell: np.ndarray, species: np.ndarray, grid
     assert (edge_index >= 0).all() and (edge_index[0] < len(mine)).all()
     o = np.lexsort((edge_index[1], edge_index[0]))
     return dict(global_ids=global_ids, species=np.asarray(species)[global_ids].astype(np.int32),
-                n_local=int(len(mine)), n_nodes=int(len(global_ids)),
+                n_local=int(len(mine)), n_nodes=int(len(global_ids)), n_interior=n_interior,
                 edge_index=edge_index[:, o], edge_vec=ev[o], ghost_owner=owner[ghosts].astype(np.int64),
                 n_global=int(len(pos)))
 
@@ -85,10 +97,12 @@ def brick_decompose(pos: np.ndarray, cell: np.ndarray, species: np.ndarray, grid
 class GhostExchange:
     """Index maps + the two collectives (forward fill, reverse sum) over torch.distributed."""
 
-    def __init__(self, part: Dict[str, np.ndarray], device, group=None):
+    def __init__(self, part: Dict[str, np.ndarray], device, group=None, engine=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group, self.device = torch, dist, group, device
+        # the CUDA engine brings its own pack / unpack kernels; the CPU stand-in of the tests uses torch ops
+        self.kernels = engine if (engine is not None and hasattr(engine, 'gather_rows')) else None
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.n_local, self.n_nodes = part['n_local'], part['n_nodes']
@@ -130,6 +144,8 @@ class GhostExchange:
         self.send_counts[self.rank] = 0
         self.n_ghost = int(sum(self.recv_counts))
         self.send_idx_all = torch.cat(self.send_idx) if self.world > 0 else torch.zeros(0, dtype=torch.int64, device=device)
+        self.send_idx32 = [i.to(torch.int32).contiguous() for i in self.send_idx]
+        self.send_idx_all32 = self.send_idx_all.to(torch.int32).contiguous()
         self._bufs = {}
 
     def _packed(self, width, dtype, device):
@@ -149,7 +165,10 @@ class GhostExchange:
             return None
         packed = self._packed(x.shape[1], x.dtype, x.device)
         if packed.shape[0] > 0:
-            self.torch.index_select(x, 0, self.send_idx_all, out=packed)
+            if self.kernels is not None:
+                self.kernels.gather_rows(x, self.send_idx_all32, packed)
+            else:
+                self.torch.index_select(x, 0, self.send_idx_all, out=packed)
         return self.dist.all_to_all_single(x[self.n_local:self.n_local + self.n_ghost], packed,
                                            output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
                                            group=self.group, async_op=async_op)
@@ -175,7 +194,10 @@ class GhostExchange:
         for q in range(self.world):
             c = self.send_counts[q]
             if c > 0:
-                g.index_add_(0, self.send_idx[q], packed[off:off + c])
+                if self.kernels is not None:
+                    self.kernels.scatter_add_rows(g, self.send_idx32[q], packed[off:off + c])
+                else:
+                    g.index_add_(0, self.send_idx[q], packed[off:off + c])
             off += c
 
     def reverse_add(self, g):
@@ -185,9 +207,10 @@ class GhostExchange:
 
 class DistributedRunner:
     """Drives one engine per rank through the stage sequence with ghost exchanges in between
-    (the protocol of ``pair_e3gnn_parallel.cpp:345-441``)."""
+    (the protocol of ``pair_e3gnn_parallel.cpp:345-441``), overlapped as the
+    module docstring describes, and -- on CUDA with NCCL -- replayed as one captured CUDA graph."""
 
-    def __init__(self, engine, part: Dict[str, np.ndarray], group=None):
+    def __init__(self, engine, part: Dict[str, np.ndarray], group=None, cuda_graph: Optional[bool] = None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
@@ -195,51 +218,113 @@ class DistributedRunner:
         self.device = engine.device
         self.n_layers = engine.spec.n_layers
         self.n_local, self.n_nodes = part['n_local'], part['n_nodes']
-        self.exchange = GhostExchange(part, self.device, group)
+        self.n_interior = int(part.get('n_interior', self.n_local))
+        self.exchange = GhostExchange(part, self.device, group, engine)
         engine.set_graph(part['species'], part['edge_index'], part['edge_vec'], n_local=self.n_local)
+        self.split = hasattr(engine, 'set_interior')
+        if self.split:
+            engine.set_interior(self.n_interior)
         self._host = None
+        on_cuda = getattr(self.device, 'type', 'cpu') == 'cuda' and dist.get_backend(group) == 'nccl'
+        self.use_graph = on_cuda if cuda_graph is None else (bool(cuda_graph) and on_cuda)
+        self._graph, self._graph_key, self.graph_error = None, None, None
+        self.graph_captures = self.graph_replays = 0
 
     def _buf(self, name, t, width):
         return self.engine.buffer(name, t, shape=(self.n_nodes, width))
 
-    def compute(self):
+    def _all_reduce_f8(self, name):
+        buf = self.engine.buffer(name, dtype='f8')
+        if not buf.numel():
+            return
+        if self.dist.get_backend(self.group) == 'nccl':
+            self.dist.all_reduce(buf, group=self.group)
+        else:
+            c = buf.cpu()
+            self.dist.all_reduce(c, group=self.group)
+            buf.copy_(c)
+
+    def _step(self):
+        """the stage sequence of one energy/force evaluation, exchanges included (eager)"""
         eng, T = self.engine, self.n_layers
         spec = eng.spec
+        split = self.split
         eng.run_stage(STAGE_FWD_BEGIN)
+        work = None
         for t in range(T):
-            eng.run_stage(STAGE_FWD_LAYER_A, t)
+            if work is None:            # layer 0: ghost features are recomputed locally, nothing in flight
+                eng.run_stage(STAGE_FWD_LAYER_A, t)
+            elif split:                 # interior atoms need no ghost row: convolve them while x(t) travels
+                eng.run_stage(STAGE_FWD_CONV_INTERIOR, t)
+                work.wait()
+                eng.run_stage(STAGE_FWD_LAYER_A2, t)
+            else:
+                work.wait()
+                eng.run_stage(STAGE_FWD_LAYER_A, t)
             work = None
-            if t + 1 < T:       # ghost rows of x(t+1) travel while the self-connection GEMM runs
+            if t + 1 < T:               # ghost rows of x(t+1) start travelling; the self-connection GEMM runs meanwhile
                 work = self.exchange.forward(self._buf('x', t + 1, spec.layers[t + 1].dim_x), async_op=True)
             eng.run_stage(STAGE_FWD_LAYER_SC, t)
-            if work is not None:
-                work.wait()
         eng.run_stage(STAGE_FWD_END)
         for t in range(T - 1, -1, -1):
-            eng.run_stage(STAGE_BWD_LAYER_A, t)
-            if t > 0:           # ghost rows of dx(t) travel back while the self-connection term is computed
+            if t == 0:
+                eng.run_stage(STAGE_BWD_LAYER_A, t)
+                continue
+            if split:                   # boundary atoms first: afterwards the ghost rows of dx(t) are final
+                eng.run_stage(STAGE_BWD_LAYER_A1, t)
                 handle = self.exchange.reverse_begin(self._buf('dx', t, spec.layers[t].dim_x))
-                eng.run_stage(STAGE_BWD_LAYER_B1, t)
-                self.exchange.reverse_finish(handle)
-                eng.run_stage(STAGE_BWD_LAYER_B2, t)
-        eng.run_stage(STAGE_BWD_END)
-        forces = eng.buffer('forces', shape=(self.n_nodes, 3))
-        self.exchange.reverse_add(forces)
-        energy = eng.buffer('energy', dtype='f8')
-        if self.dist.get_backend(self.group) == 'nccl':
-            self.dist.all_reduce(energy, group=self.group)
-        else:
-            e = energy.cpu()
-            self.dist.all_reduce(e, group=self.group)
-            energy.copy_(e)
-        virial = eng.buffer('virial', dtype='f8')
-        if virial.numel():
-            if self.dist.get_backend(self.group) == 'nccl':
-                self.dist.all_reduce(virial, group=self.group)
+                eng.run_stage(STAGE_BWD_LAYER_A2, t)
             else:
-                v = virial.cpu()
-                self.dist.all_reduce(v, group=self.group)
-                virial.copy_(v)
+                eng.run_stage(STAGE_BWD_LAYER_A, t)
+                handle = self.exchange.reverse_begin(self._buf('dx', t, spec.layers[t].dim_x))
+            eng.run_stage(STAGE_BWD_LAYER_B1, t)
+            self.exchange.reverse_finish(handle)
+            eng.run_stage(STAGE_BWD_LAYER_B2, t)
+        eng.run_stage(STAGE_BWD_END)
+        self.exchange.reverse_add(eng.buffer('forces', shape=(self.n_nodes, 3)))
+        self._all_reduce_f8('energy')
+        self._all_reduce_f8('virial')
+
+    def _key(self):
+        eng = self.engine
+        return (self.n_nodes, self.n_local, int(eng.n_edges), eng.buffer('forces', shape=(self.n_nodes, 3)).data_ptr(),
+                self._buf('x', self.n_layers - 1, eng.spec.layers[-1].dim_x).data_ptr())
+
+    def _capture(self):
+        """capture the step (kernels + NCCL) into a CUDA graph; any failure falls back to eager stages"""
+        torch = self.torch
+        try:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):      # warm-up on the capture stream (NCCL channels, lazy allocations)
+                    self._step()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._step()
+            self._graph, self._graph_key = g, self._key()
+            self.graph_captures += 1
+        except Exception as ex:   # noqa: BLE001
+            self.graph_error = f'{type(ex).__name__}: {ex}'[:300]
+            self._graph, self.use_graph = None, False
+            torch.cuda.synchronize(self.device)
+
+    def set_cuda_graph(self, enable: bool):
+        on_cuda = getattr(self.device, 'type', 'cpu') == 'cuda' and self.dist.get_backend(self.group) == 'nccl'
+        self.use_graph = bool(enable) and on_cuda and self.graph_error is None
+
+    def compute(self):
+        if self.use_graph:
+            if self._graph is None or self._graph_key != self._key():
+                self._graph = None
+                self._capture()
+            if self._graph is not None:
+                self._graph.replay()
+                self.graph_replays += 1
+                return self
+        self._step()
         return self
 
     def results(self):
@@ -282,6 +367,8 @@ class DistributedRunner:
         for k in ('species', 'rowptr', 'src', 'vec'):
             d[k].copy_(h[k], non_blocking=True)
         self.engine.set_graph_csr(d['species'], d['rowptr'], d['src'], d['vec'], self.n_local)
+        if self.split:
+            self.engine.set_interior(self.n_interior)
         self.compute()
         h['f_out'].copy_(self.engine.buffer('forces', shape=(self.n_nodes, 3))[:self.n_local], non_blocking=True)
         h['e_out'].copy_(self.engine.buffer('energy', dtype='f8'), non_blocking=True)

@@ -11,9 +11,10 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sevenn_b200.engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B, STAGE_BWD_LAYER_B1,
-                                STAGE_BWD_LAYER_B2, STAGE_FWD_BEGIN, STAGE_FWD_END, STAGE_FWD_LAYER,
-                                STAGE_FWD_LAYER_A, STAGE_FWD_LAYER_SC)
+from sevenn_b200.engine import (STAGE_BWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_A1, STAGE_BWD_LAYER_A2,
+                                STAGE_BWD_LAYER_B, STAGE_BWD_LAYER_B1, STAGE_BWD_LAYER_B2, STAGE_FWD_BEGIN,
+                                STAGE_FWD_CONV_INTERIOR, STAGE_FWD_END, STAGE_FWD_LAYER, STAGE_FWD_LAYER_A,
+                                STAGE_FWD_LAYER_A2, STAGE_FWD_LAYER_SC)
 from sevenn_b200.neighbors import build_graph, diamond_si, rocksalt_nacl
 from sevenn_b200.parallel import DistributedRunner, brick_decompose
 
@@ -54,6 +55,10 @@ class FakeEngine:
         self.energy = torch.zeros(1, dtype=torch.float64)
         self.virial = torch.zeros(6, dtype=torch.float64)
         self.dEdw = torch.zeros(len(self.w), dtype=torch.float64)
+        self.n_interior = self.n_local
+
+    def set_interior(self, n_interior):
+        self.n_interior = int(n_interior)
 
     def buffer(self, name, t=0, dtype='f4', shape=None):
         return {'x': lambda: self.x[t], 'dx': lambda: self.dx, 'forces': lambda: self.forces,
@@ -67,8 +72,19 @@ class FakeEngine:
             self.dEdw.zero_()
         elif stage in (STAGE_FWD_LAYER_SC, STAGE_BWD_LAYER_B1):
             pass        # the stand-in has no self-connection term
-        elif stage in (STAGE_FWD_LAYER, STAGE_FWD_LAYER_A):
-            a = torch.zeros(nl, self.D, dtype=torch.float64).index_add_(0, self.dst, self.w[:, None] * self.x[t][self.src])
+        elif stage in (STAGE_FWD_LAYER, STAGE_FWD_LAYER_A, STAGE_FWD_CONV_INTERIOR, STAGE_FWD_LAYER_A2):
+            # centre ranges as in the CUDA engine: interior = [0, n_interior), boundary = the rest
+            m = torch.ones_like(self.dst, dtype=torch.bool)
+            if stage == STAGE_FWD_CONV_INTERIOR:
+                m = self.dst < self.n_interior
+                assert bool((self.src[m] < nl).all())       # interior atoms never read a ghost row
+            elif stage == STAGE_FWD_LAYER_A2:
+                m = self.dst >= self.n_interior
+            part = torch.zeros(nl, self.D, dtype=torch.float64).index_add_(0, self.dst[m], self.w[m, None] * self.x[t][self.src[m]])
+            if stage == STAGE_FWD_CONV_INTERIOR:
+                self.a[t] = part
+                return
+            a = part if stage != STAGE_FWD_LAYER_A2 else self.a[t] + part
             self.a[t] = a
             self.h = torch.tanh(a)
             if t + 1 < self.T:
@@ -76,12 +92,19 @@ class FakeEngine:
         elif stage == STAGE_FWD_END:
             self.energy[0] = self.h.sum()
             self.dh = torch.ones(nl, self.D, dtype=torch.float64)
-        elif stage == STAGE_BWD_LAYER_A:
-            da = self.dh * (1 - torch.tanh(self.a[t]) ** 2)
-            self.dEdw += (da[self.dst] * self.x[t][self.src]).sum(1)
-            self.dx.zero_()
+        elif stage in (STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_A1, STAGE_BWD_LAYER_A2):
+            m = torch.ones_like(self.dst, dtype=torch.bool)
+            if stage == STAGE_BWD_LAYER_A1:
+                m = self.dst >= self.n_interior
+            elif stage == STAGE_BWD_LAYER_A2:
+                m = self.dst < self.n_interior
+            if stage != STAGE_BWD_LAYER_A2:
+                self.da = self.dh * (1 - torch.tanh(self.a[t]) ** 2)
+                self.dx.zero_()
+            da = self.da
+            self.dEdw[m] += (da[self.dst[m]] * self.x[t][self.src[m]]).sum(1)
             if t > 0:
-                self.dx.index_add_(0, self.src, self.w[:, None] * da[self.dst])
+                self.dx.index_add_(0, self.src[m], self.w[m, None] * da[self.dst[m]])
         elif stage in (STAGE_BWD_LAYER_B, STAGE_BWD_LAYER_B2):
             self.dh = self.coef[t - 1] * self.dx[:nl]
         elif stage == STAGE_BWD_END:
@@ -103,6 +126,8 @@ def _free_port():
 def _system(kind):
     if kind == 'si':
         pos, cell, z = diamond_si(3, 2, 2, seed=4)
+    elif kind == 'si_long':                                  # bricks wide enough to have interior atoms
+        pos, cell, z = diamond_si(6, 2, 2, seed=5)
     else:
         pos, cell, z = rocksalt_nacl(2, 2, 2, sigma=0.08, seed=7)
     species = (z == z.min()).astype(np.int32)
@@ -116,16 +141,25 @@ def _worker(rank, world, port, grid, kind, q):
     try:
         pos, cell, species = _system(kind)
         part = brick_decompose(pos, cell, species, grid, rank, 5.0)
+        assert 0 <= part['n_interior'] <= part['n_local']
+        nl, ni = part['n_local'], part['n_interior']
+        ghost_edge = part['edge_index'][1] >= nl
+        assert (part['edge_index'][0][ghost_edge] >= ni).all()       # only boundary atoms have ghost neighbours
+        assert set(np.unique(part['edge_index'][0][ghost_edge])) == set(range(ni, nl)) or ni == nl
         eng = FakeEngine()
         run = DistributedRunner(eng, part)
+        assert run.split
         run.compute()
+        if kind == 'si_long':
+            assert 0 < ni < nl
         q.put((rank, part['global_ids'][:part['n_local']], eng.forces[:part['n_local']].numpy().copy(),
                float(eng.energy[0]), part['edge_index'].shape[1], part['n_nodes'] - part['n_local']))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,grid,kind', [(2, (2, 1, 1), 'si'), (2, (1, 1, 2), 'nacl'), (4, (2, 2, 1), 'si')])
+@pytest.mark.parametrize('world,grid,kind', [(2, (2, 1, 1), 'si'), (2, (1, 1, 2), 'nacl'), (4, (2, 2, 1), 'si'),
+                                             (2, (2, 1, 1), 'si_long')])
 def test_distributed_protocol_matches_serial(world, grid, kind):
     pos, cell, species = _system(kind)
     ei, ev = build_graph(pos, cell, True, 5.0)

@@ -34,9 +34,19 @@ def _worker(rank, world, port, grid, model, q):
         pos, cell, z = diamond_si(4, 3, 3, seed=2)
         part = brick_decompose(pos, cell, species_of(meta, z), grid, rank, 5.0)
         run = DistributedRunner(B200Engine(meta, arrays, device=rank), part)
-        run.compute()
+        run.set_cuda_graph(False)
+        run.compute()                       # eager stage sequence (split convolutions, overlapped exchanges)
+        torch.cuda.synchronize()
+        r_eager = run.results()
+        run.set_cuda_graph(True)
+        for _ in range(3):                  # capture, then replays of the whole step incl. the NCCL calls
+            run.compute()
         torch.cuda.synchronize()
         r = run.results()
+        assert run.graph_error is None, run.graph_error
+        assert run.graph_captures == 1 and run.graph_replays == 3
+        assert abs(float(r['energy'].cpu()[0]) - float(r_eager['energy'].cpu()[0])) < 1e-9
+        assert torch.allclose(r['forces'], r_eager['forces'], atol=2e-6)
         h = run.compute_host()
         q.put((rank, r['global_ids'], r['forces'].cpu().numpy(), float(r['energy'].cpu()[0]),
                r['atomic_energy'].cpu().numpy(), r['virial'].cpu().numpy(), h['energy'], h['forces'].copy()))
