@@ -117,6 +117,13 @@ S7B_API int s7b_gather_rows(const float* src, int32_t ld_src, const int32_t* idx
 S7B_API int s7b_scatter_add_rows(float* dst, int32_t ld_dst, const int32_t* idx, int64_t n, int32_t width,
                                  const float* in, void* stream);
 
+/* One block-diagonal irreps linear C_l (+)= A_l W_l, l = 0..n_l-1 (block l: 2l+1 rows per node, component-
+ * major rows of K_l / N_l floats at a_off[l] / c_off[l] inside node rows of lda / ldc floats) through the
+ * engine's own kernels: use_tc = 1 the tcgen05 path, 0 the FP32 SIMT kernel.  A, C device; W host. */
+S7B_API int s7b_block_linear(const float* A, int32_t lda, int32_t n_nodes, int32_t n_l, const int32_t* a_off,
+                             const int32_t* a_K, const float* W_host, float* C, int32_t ldc, const int32_t* c_off,
+                             const int32_t* c_N, int32_t accumulate, int32_t use_tc, void* stream);
+
 /* Host-only helper (no GPU needed): the weight packing of the tensor-core linear for one [K, N] block --
  * three signed 8-bit fixed-point slices per weight as bf16, in the shared-memory layout the kernel
  * consumes (sevenn_b200/csrc/tc_gemm.cuh).  q: 3*K*N uint16, fb: N column scales, *NT: tile width. */
@@ -132,7 +139,7 @@ S7B_API void s7b_engine_destroy(S7bEngine* eng);
 S7B_API int s7b_engine_set_atomic_virial(S7bEngine* eng, int enable);
 
 /* Upload one named parameter array (host pointer, fp32).  Names: "embed_x0", "embed_g0",
- * "readout", "scale", "shift", "bessel", and per layer t "si1", "si1T", "sc", "scT", "si2",
+ * "readout" (+ optional "readout_lo", the fp32 residual of the fp64 fold), "scale", "shift", "bessel", and per layer t "si1", "si1T", "sc", "scT", "si2",
  * "si2T", "table", "mlp0".."mlp2", "mlp0T".."mlp2T" (layouts: sevenn_b200/engine.py). */
 S7B_API int s7b_engine_set_param(S7bEngine* eng, const char* name, int layer, const float* host, size_t numel);
 
@@ -213,6 +220,48 @@ S7B_API int s7b_conv_backward(const S7bConvPlan* plan, const float* x, const flo
                       const int32_t* rowptr, const int32_t* src, int32_t n_nodes, int32_t n_dst,
                       int64_t n_edges, const float* grad_out, float* grad_x, float* grad_sh,
                       float* grad_weight, void* stream);
+
+/* ---- D3 dispersion correction ------------------------------------------------------
+ * Cell-list DFT-D3 (zero / Becke-Johnson damping) replacing the reference's all-pairs CUDA code
+ * sevenn/pair_e3gnn/pair_d3.cu / pair_d3_for_ase.cu (kernels :765-845, 1004-1058, 1263-1745, 1797-1962).
+ * Native interface: tables reduced to the system's atom types (sevenn_b200/d3.py does what
+ * PairD3::coeff, :633-845, does), positions / cell rows in Angstrom, types 0-based.  Stages operate on an
+ * atom range of the bin-sorted order so that several GPUs can share one system (atom decomposition with
+ * replicated positions; the caller all-gathers "cn" after stage 1 and "dc6i" after stage 2):
+ *   1 = coordination numbers, 2 = C6 weights of all atoms + pair energy / forces / dE/dCN of the range,
+ *   3 = chain-rule forces through the coordination numbers. */
+typedef struct S7bD3 S7bD3;
+S7B_API int s7b_d3_create(S7bD3** out);
+S7B_API void s7b_d3_destroy(S7bD3* d3);
+S7B_API int s7b_d3_set_params(S7bD3* d3, int32_t ntypes, const double* rcov, const double* r2r4, const double* r0ab,
+                              const double* c6ref, const double* cnref, const int32_t* mxc);
+/* damping: 0 = zero, 1 = Becke-Johnson; cutoffs are squared distances in bohr^2 (reference defaults 9000 / 1600) */
+S7B_API int s7b_d3_set_damping(S7bD3* d3, int32_t damping, double s6, double s8, double a1, double a2, double alp6,
+                               double alp8, double vdw_cutoff_au2, double cn_cutoff_au2);
+S7B_API int s7b_d3_set_system(S7bD3* d3, int32_t n_atoms, const int32_t* types, const double* positions,
+                              const double* cell9, const int32_t* pbc3, void* stream);
+S7B_API int s7b_d3_run_stage(S7bD3* d3, int32_t stage, int32_t i_begin, int32_t i_end, void* stream);
+/* device buffers in bin-sorted order: "cn", "dc6i" double[n]; "force" double[n,3] (hartree/bohr); "energy"
+ * double[1]; "sigma" double[6]; "order" int32[n] (sorted position -> caller's atom index) */
+S7B_API void* s7b_d3_buffer(S7bD3* d3, const char* name, size_t* numel);
+/* energy (eV), forces [n,3] (eV/A, caller's atom order), sigma6 (eV: xx,yy,zz,xy,xz,yz of sum f (x) r) */
+S7B_API int s7b_d3_results_host(S7bD3* d3, double* energy, double* forces, double* sigma6, void* stream);
+S7B_API int s7b_d3_compute_host(S7bD3* d3, double* energy, double* forces, double* sigma6, void* stream);
+
+/* The reference's own D3 entry points (pair_d3_for_ase.cu:2034-2082; ctypes signatures sevenn/calculator.py:430-483),
+ * same names / arguments / call order, so its D3Calculator can load this library in place of pair_d3.so.
+ * Tables: weights/d3_params.bin next to the repository's library, or $S7B_D3_PARAMS. */
+S7B_API S7bD3* pair_init(void);
+S7B_API void pair_set_atom(S7bD3* pair, int natoms, int ntypes, int* type, double* x_flat);
+S7B_API void pair_set_domain(S7bD3* pair, int xperiodic, int yperiodic, int zperiodic, double* boxlo, double* boxhi,
+                             double xy, double xz, double yz);
+S7B_API void pair_run_settings(S7bD3* pair, double rthr, double cnthr, const char* damp_name, const char* func_name);
+S7B_API void pair_run_coeff(S7bD3* pair, int* atomic_numbers);
+S7B_API void pair_run_compute(S7bD3* pair);
+S7B_API double pair_get_energy(S7bD3* pair);
+S7B_API double* pair_get_force(S7bD3* pair);
+S7B_API double* pair_get_stress(S7bD3* pair);
+S7B_API void pair_fin(S7bD3* pair);
 
 #ifdef __cplusplus
 }

@@ -698,6 +698,41 @@ int s7b_dense_linear(const float* A, const float* W, float* C, int64_t rows, int
   return rc;
 }
 
+// Test / utility entry: one block-diagonal irreps linear  C_l (+)= A_l W_l  (l = 0..n_l-1, block l has 2l+1
+// rows per node) through the engine's GEMM kernels -- use_tc = 1: the tensor-core path exactly as the
+// engine drives it (row exponents, packed weights, tensor maps), 0: the FP32 SIMT kernel.  A, C device
+// pointers; W host pointer (blocks [K_l, N_l] row-major, concatenated).
+int s7b_block_linear(const float* A, int32_t lda, int32_t n_nodes, int32_t n_l, const int32_t* a_off, const int32_t* a_K,
+                     const float* W_host, float* C, int32_t ldc, const int32_t* c_off, const int32_t* c_N,
+                     int32_t accumulate, int32_t use_tc, void* stream) {
+  if (!A || !C || !W_host || !a_off || !a_K || !c_off || !c_N) return fail("null argument");
+  if (n_l < 1 || n_l > kMaxL || n_nodes < 1) return fail("bad sizes");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  size_t wn = 0;
+  for (int l = 0; l < n_l; ++l) wn += (size_t)a_K[l] * c_N[l];
+  int rc = 0;
+  if (use_tc) {
+    TcWeights w;
+    RowExp re;
+    rc = tc_build_weights(w, W_host, a_K, c_N, n_l);
+    if (!rc && !w.ok) rc = fail("shapes not supported by the tensor-core linear");
+    if (!rc) rc = launch_row_exponents(re, A, lda, a_off, a_K, n_l, n_nodes, st);
+    if (!rc) rc = launch_tc_linear(w, re, A, lda, a_off, a_K, C, ldc, c_off, c_N, n_l, n_nodes, accumulate != 0, st);
+    cudaStreamSynchronize(st);
+    w.q.release();
+    w.fb.release();
+    re.buf.release();
+  } else {
+    float* dW = nullptr;
+    S7B_CUDA_CHECK(cudaMalloc((void**)&dW, wn * sizeof(float)));
+    cudaMemcpy(dW, W_host, wn * sizeof(float), cudaMemcpyHostToDevice);
+    rc = irreps_linear(A, lda, a_off, a_K, C, ldc, c_off, c_N, n_l, dW, n_nodes, accumulate != 0, st);
+    cudaStreamSynchronize(st);
+    cudaFree(dW);
+  }
+  return rc;
+}
+
 // Host-only: the tensor-core weight packing of tc_gemm.cuh for one [K, N] block (tests/test_tc_pack_cpu.py).
 // q: 3*K*N uint16 (bf16 bits), laid out [n tile][K/32][slice][canonical NT x 32]; fb: N floats; *NT_out = tile width.
 int s7b_tc_pack_weights(const float* W, int32_t K, int32_t N, uint16_t* q, float* fb, int32_t* NT_out) {
@@ -910,6 +945,9 @@ int s7b_engine_set_graph(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t
   rc |= e->dh.ensure(Nl * std::max(max_h, max_x) * sizeof(float));
   rc |= e->dg.ensure(Nl * max_g * sizeof(float));
   rc |= e->dx.ensure(Nn * max_x * sizeof(float));
+  // row exponents of the tensor-core GEMM inputs (at most 1+3+5+7 rows per node); sized here because the
+  // step may be recorded into a CUDA graph, where cudaMalloc is not allowed
+  for (RowExp* r : {&e->re_mid, &e->re_h, &e->re_dg, &e->re_dx}) rc |= r->buf.ensure(Nn * 16 * sizeof(int));
   rc |= e->energy.ensure(sizeof(double));
   rc |= e->virial.ensure(6 * sizeof(double));
   rc |= e->atomic_energy.ensure(Nl * sizeof(float));
@@ -1087,7 +1125,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       if (Nl > 0) {
         const int blk = 256;
         ProfScope ps(e->prof, st, "readout");
-        readout_kernel<<<(Nl * 32 + blk - 1) / blk, blk, 0, st>>>(e->h.as<float>(), wr, scale, shift, e->d_species, Nl, L.dim_h, e->atomic_energy.as<float>(), e->energy.as<double>(), e->dh.as<float>());
+        readout_kernel<<<(Nl * 32 + blk - 1) / blk, blk, 0, st>>>(e->h.as<float>(), wr, gparam(e, "readout_lo"), scale, shift, e->d_species, Nl, L.dim_h, e->atomic_energy.as<float>(), e->energy.as<double>(), e->dh.as<float>());
         S7B_LAUNCH_CHECK();
       }
       return 0;

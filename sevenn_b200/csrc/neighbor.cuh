@@ -37,7 +37,7 @@ __device__ __forceinline__ void nl_frac(const NLGrid& g, const double* p, double
 }
 
 // bin key per atom + wrapped cartesian position
-__global__ void nl_bin_kernel(const NLGrid g, const double* __restrict__ pos, int n, int* __restrict__ key,
+static __global__ void nl_bin_kernel(const NLGrid g, const double* __restrict__ pos, int n, int* __restrict__ key,
                               int* __restrict__ idx, double* __restrict__ wrapped) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -58,7 +58,7 @@ __global__ void nl_bin_kernel(const NLGrid g, const double* __restrict__ pos, in
 }
 
 // first sorted position of every bin (bin_start[nbins] = n)
-__global__ void nl_bin_start_kernel(const int* __restrict__ key_sorted, int n, int nbins, int* __restrict__ bin_start) {
+static __global__ void nl_bin_start_kernel(const int* __restrict__ key_sorted, int n, int nbins, int* __restrict__ bin_start) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s > n) return;
   const int prev = (s == 0) ? -1 : key_sorted[s - 1];

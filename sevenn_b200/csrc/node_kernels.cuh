@@ -270,9 +270,12 @@ __global__ void scatter_add_rows_idx_kernel(float* __restrict__ dst, int ld_dst,
   }
 }
 
-// Readout (two bias-free linears folded into one vector wr), species-wise rescale, energy sum and
-// the seed of the backward pass dE/dh = scale[s] * wr.  One warp per atom.
+// Readout (two bias-free linears folded into one vector wr = wr_hi + wr_lo, the fp32 pair of the fp64
+// fold), species-wise rescale, energy sum and the seed of the backward pass dE/dh = scale[s] * wr.
+// One warp per atom; the 128-term dot product, the rescale and the energy sum run in double so that the
+// per-atom energy carries no parameter-rounding offset (identical atoms would all share its sign).
 __global__ void readout_kernel(const float* __restrict__ h, const float* __restrict__ wr,
+                               const float* __restrict__ wr_lo,
                                const float* __restrict__ scale, const float* __restrict__ shift,
                                const int* __restrict__ species, int n_nodes, int width,
                                float* __restrict__ atomic_energy, double* __restrict__ energy,
@@ -284,18 +287,19 @@ __global__ void readout_kernel(const float* __restrict__ h, const float* __restr
     const float* row = h + (size_t)warp * width;
     const int s = __ldg(species + warp);
     const float sc = __ldg(scale + s);
-    float acc = 0.0f;
+    double acc = 0.0;
     for (int c = lane; c < width; c += 32) {
       const float w = __ldg(wr + c);
-      acc = fmaf(row[c], w, acc);
+      const double wd = (double)w + (wr_lo != nullptr ? (double)__ldg(wr_lo + c) : 0.0);
+      acc = fma((double)row[c], wd, acc);
       dh[(size_t)warp * width + c] = sc * w;
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    const float ea = fmaf(sc, acc, __ldg(shift + s));
+    const double ea = fma((double)sc, acc, (double)__ldg(shift + s));
     if (lane == 0) {
-      atomic_energy[warp] = ea;
-      e_atom = (double)ea;
+      atomic_energy[warp] = (float)ea;
+      e_atom = ea;
     }
   }
   // block reduction in double, one atomic per block

@@ -16,14 +16,16 @@
 // (the dropped A1*B2, A2*B1, A2*B2 are < 2^-24 relative).  Six kind::f16 (bf16) MMAs per K = 16 step cost
 // the same tensor time as 3xTF32.  Emulated bit for bit on the CPU by tests/test_tc_pack_cpu.py.
 //
-// Structure (persistent, one CTA per SM, 320 threads, tiles of 128 rows x NT <= 128 columns):
-//   warp 8   TMA producer: per 32-wide K chunk one cp.async.bulk.tensor (3-D map over (k, component,
-//            node); 128B swizzle) for the raw fp32 A tile and one cp.async.bulk for the pre-sliced,
-//            pre-arranged W chunk, both completing on the stage's mbarrier (3-stage ring)
-//   warps 0-3 transform: thread r converts row r of the raw tile into the three bf16 slices, written in
-//            the canonical K-major UMMA layout (8-row x 16-byte core matrices)
+// Structure (persistent, one CTA per SM, 352 threads, tiles of 128 rows x NT <= 128 columns):
+//   warp 8   TMA producer A: per 32-wide K chunk one cp.async.bulk.tensor (3-D map over (k, component,
+//            node); 128B swizzle) for the raw fp32 A tile into a 5-deep ring (the HBM/L2 round trip of
+//            these loads is what bounds the kernel: 80 KB in flight per SM)
+//   warp 10  TMA producer W: one cp.async.bulk per chunk for the pre-sliced, pre-arranged W chunk (3-deep ring)
+//   warps 0-3 transform: thread r pulls row r of a raw chunk into registers (freeing its slot), converts it
+//            into the three bf16 slices and writes them in the canonical K-major UMMA layout (8-row x
+//            16-byte core matrices) into a 2-deep operand ring
 //   warp 9   MMA issuer: one thread issues 12 tcgen05.mma per chunk (M = 128, N = NT, K = 16) into the
-//            two TMEM accumulators of the tile; tcgen05.commit frees the stage / publishes the tile
+//            two TMEM accumulators of the tile; tcgen05.commit frees the operand slots / publishes the tile
 //   warps 4-7 epilogue: tcgen05.ld the accumulators (double-buffered in TMEM, so the next tile's MMAs
 //            overlap), scale, transpose a 32x32 slab through shared memory and write/accumulate C with
 //            128-byte coalesced row segments.
@@ -39,14 +41,20 @@ namespace s7b {
 constexpr int kTcBM = 128;          // rows (nodes) per tile
 constexpr int kTcKC = 32;           // K elements per pipeline stage
 constexpr int kTcMaxNT = 128;       // columns per tile (two accumulators x two buffers = 512 TMEM columns)
-constexpr int kTcStages = 3;
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 352;     // 4 transform + 4 epilogue warps, A producer, MMA issuer, W producer
 constexpr int kTcRawBytes = kTcBM * kTcKC * 4;            // 16 KB raw fp32 A chunk
 constexpr int kTcASliceBytes = kTcBM * kTcKC * 2;         // 8 KB per bf16 slice
 constexpr int kTcBSliceBytes = kTcMaxNT * kTcKC * 2;      // 8 KB per bf16 slice (NT = 128)
-constexpr int kTcStageBytes = kTcRawBytes + 3 * kTcASliceBytes + 3 * kTcBSliceBytes;   // 64 KB
+// three decoupled rings: raw A chunks (deep: the HBM/L2 round trip of the TMA loads is what has to be
+// hidden), sliced A operands and sliced W operands (both released by tcgen05.commit)
+constexpr int kTcRawStages = 5, kTcOpsStages = 2, kTcWStages = 3;
+constexpr int kTcOpsBytes = 3 * kTcASliceBytes, kTcWBytes = 3 * kTcBSliceBytes;
+constexpr int kTcRawOff = 0;
+constexpr int kTcOpsOff = kTcRawOff + kTcRawStages * kTcRawBytes;
+constexpr int kTcWOff = kTcOpsOff + kTcOpsStages * kTcOpsBytes;
+constexpr int kTcEpiOff = kTcWOff + kTcWStages * kTcWBytes;
 constexpr int kTcEpiBytes = 4 * 32 * 33 * 4;              // per-warp 32 x 33 transpose scratch
-constexpr int kTcSmemBytes = kTcStages * kTcStageBytes + kTcEpiBytes + 1024 /*alignment slack*/;
+constexpr int kTcSmemBytes = kTcEpiOff + kTcEpiBytes + 1024 /*alignment slack*/;
 constexpr int kTcZeroRow = -1000;   // row exponent of an all-zero row
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -68,6 +76,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive that carries a data dependency on `dep`: the arrival cannot issue before the value is in its
+// register, i.e. before the shared-memory loads that produced it have returned (releasing a slot that was
+// read with plain loads: the refill by the TMA engine must not overtake them)
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, float dep) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 t;\n"
+      "mov.b32 t, %1;\n"
+      "mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)), "f"(dep) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -200,7 +219,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar_full_raw[kTcStages], bar_full_ops[kTcStages], bar_empty[kTcStages];
+  __shared__ uint64_t bar_raw_full[kTcRawStages], bar_raw_empty[kTcRawStages];
+  __shared__ uint64_t bar_ops_full[kTcOpsStages], bar_ops_empty[kTcOpsStages];
+  __shared__ uint64_t bar_w_full[kTcWStages], bar_w_empty[kTcWStages];
   __shared__ uint64_t bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t tmem_base_sh;
 
@@ -211,15 +232,10 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < kTcStages; ++s) {
-      mbar_init(&bar_full_raw[s], 1);
-      mbar_init(&bar_full_ops[s], 128);
-      mbar_init(&bar_empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_acc_full[b], 1);
-      mbar_init(&bar_acc_empty[b], 128);
-    }
+    for (int s = 0; s < kTcRawStages; ++s) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], 128); }
+    for (int s = 0; s < kTcOpsStages; ++s) { mbar_init(&bar_ops_full[s], 128); mbar_init(&bar_ops_empty[s], 1); }
+    for (int s = 0; s < kTcWStages; ++s) { mbar_init(&bar_w_full[s], 1); mbar_init(&bar_w_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -238,9 +254,32 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
     ci = r2 % a.blk[b].d;
     mt = r2 / a.blk[b].d;
   };
+  auto row_exp = [&](int t, int row) -> int {           // row exponent of tile t's row (kTcZeroRow beyond the nodes)
+    if (t >= a.n_tiles) return kTcZeroRow;
+    int b, mt, ci, nt;
+    decode(t, b, mt, ci, nt);
+    const int node = mt * kTcBM + row;
+    return node < a.n_nodes ? __ldg(a.E + (size_t)node * a.rows_per_node + a.blk[b].row_base + ci) : kTcZeroRow;
+  };
 
   if (warp == 8) {
-    // =================== TMA producer ===================
+    // =================== TMA producer, A: raw fp32 chunks ===================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        int b, mt, ci, nt;
+        decode(t, b, mt, ci, nt);
+        const int n_kc = a.blk[b].K / kTcKC;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int s = it % kTcRawStages;
+          mbar_wait(&bar_raw_empty[s], ((it / kTcRawStages) & 1) ^ 1);
+          mbar_expect_tx(&bar_raw_full[s], (uint32_t)kTcRawBytes);
+          tma_load_3d(smem + kTcRawOff + (size_t)s * kTcRawBytes, &maps.m[b], kc * kTcKC, ci, mt * kTcBM, &bar_raw_full[s]);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // =================== TMA producer, W: pre-sliced bf16 chunks ===================
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
@@ -251,44 +290,47 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         const uint32_t b_bytes = 3u * (uint32_t)B.NT * kTcKC * 2u;
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(B.Wq) + (size_t)nt * n_kc * b_bytes;
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
-          const int s = it % kTcStages;
-          mbar_wait(&bar_empty[s], ((it / kTcStages) & 1) ^ 1);
-          uint8_t* st = smem + (size_t)s * kTcStageBytes;
-          mbar_expect_tx(&bar_full_raw[s], (uint32_t)kTcRawBytes + b_bytes);
-          tma_load_3d(st, &maps.m[b], kc * kTcKC, ci, mt * kTcBM, &bar_full_raw[s]);
-          bulk_load(st + kTcRawBytes + 3 * kTcASliceBytes, wsrc + (size_t)kc * b_bytes, b_bytes, &bar_full_raw[s]);
+          const int s = it % kTcWStages;
+          mbar_wait(&bar_w_empty[s], ((it / kTcWStages) & 1) ^ 1);
+          mbar_expect_tx(&bar_w_full[s], b_bytes);
+          bulk_load(smem + kTcWOff + (size_t)s * kTcWBytes, wsrc + (size_t)kc * b_bytes, b_bytes, &bar_w_full[s]);
         }
       }
     }
   } else if (warp < 4) {
     // =================== transform: raw fp32 row -> three bf16 slices ===================
     const int r = tid;                                  // row of the tile
+    const uint32_t swz = a.swizzle ? (uint32_t)(r & 7) : 0u;
+    const uint32_t row_off = (uint32_t)((r & 7) * 16 + (r >> 3) * 512);
+    const float M = 12582912.0f;                        // 1.5 * 2^23: (x + M) - M = rint(x)
     uint32_t it = 0;
+    int Ea_next = row_exp(blockIdx.x, r);
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
       int b, mt, ci, nt;
       decode(t, b, mt, ci, nt);
-      const TcLinBlock& B = a.blk[b];
-      const int n_kc = B.K / kTcKC;
-      const int node = mt * kTcBM + r;
-      int Ea = kTcZeroRow;
-      if (node < a.n_nodes) Ea = __ldg(a.E + (size_t)node * a.rows_per_node + B.row_base + ci);
+      const int n_kc = a.blk[b].K / kTcKC;
+      const int Ea = Ea_next;
+      Ea_next = row_exp(t + gridDim.x, r);              // in flight while this tile is converted
       const float sc = (Ea == kTcZeroRow) ? 0.0f : exp2i(23 - Ea);     // t = a * sc, |t| < 2^23
-      const float M = 12582912.0f;                                      // 1.5 * 2^23: (x + M) - M = rint(x)
-      const uint32_t swz = a.swizzle ? (uint32_t)(r & 7) : 0u;
       for (int kc = 0; kc < n_kc; ++kc, ++it) {
-        const int s = it % kTcStages;
-        mbar_wait(&bar_full_raw[s], (it / kTcStages) & 1);
-        uint8_t* st = smem + (size_t)s * kTcStageBytes;
-        const uint8_t* raw = st + (size_t)r * 128;
-        uint8_t* a0 = st + kTcRawBytes;
+        const int s = it % kTcRawStages, o = it % kTcOpsStages;
+        mbar_wait(&bar_raw_full[s], (it / kTcRawStages) & 1);
+        const uint8_t* raw = smem + kTcRawOff + (size_t)s * kTcRawBytes + (size_t)r * 128;
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(raw + (((uint32_t)q ^ swz) << 4));
+        float dep = v[0].x;                             // touches every load: all eight have returned
+#pragma unroll
+        for (int q = 1; q < 8; ++q) dep += v[q].x;
+        mbar_arrive_after(&bar_raw_empty[s], dep);      // the raw chunk is in registers: its slot can be refilled
+        mbar_wait(&bar_ops_empty[o], ((it / kTcOpsStages) & 1) ^ 1);
+        uint8_t* a0 = smem + kTcOpsOff + (size_t)o * kTcOpsBytes;
         uint8_t* a1 = a0 + kTcASliceBytes;
         uint8_t* a2 = a1 + kTcASliceBytes;
-        const uint32_t row_off = (uint32_t)((r & 7) * 16 + (r >> 3) * 512);
 #pragma unroll
         for (int kq = 0; kq < 4; ++kq) {                // 8 consecutive k = one 16-byte core-matrix row
-          const float4 v0 = *reinterpret_cast<const float4*>(raw + (((uint32_t)(2 * kq) ^ swz) << 4));
-          const float4 v1 = *reinterpret_cast<const float4*>(raw + (((uint32_t)(2 * kq + 1) ^ swz) << 4));
-          const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          const float x[8] = {v[2 * kq].x, v[2 * kq].y, v[2 * kq].z, v[2 * kq].w,
+                              v[2 * kq + 1].x, v[2 * kq + 1].y, v[2 * kq + 1].z, v[2 * kq + 1].w};
           float s0[8], s1[8], s2[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -308,7 +350,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
           *reinterpret_cast<uint4*>(a2 + off) = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
         }
         fence_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(&bar_full_ops[s]);
+        mbar_arrive(&bar_ops_full[o]);
       }
     }
   } else if (warp == 9) {
@@ -323,16 +365,17 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         const int buf = tile_it & 1;
         mbar_wait(&bar_acc_empty[buf], ((tile_it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 * B.NT);
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 * kTcMaxNT)   /* fixed halves: tiles of different NT alternate */;
         const uint32_t acc1 = acc0 + (uint32_t)B.NT;
         const uint32_t idesc = umma_idesc_bf16(B.NT);
         const uint32_t b_slice = (uint32_t)B.NT * kTcKC * 2u;
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
-          const int s = it % kTcStages;
-          mbar_wait(&bar_full_ops[s], (it / kTcStages) & 1);
+          const int o = it % kTcOpsStages, w = it % kTcWStages;
+          mbar_wait(&bar_w_full[w], (it / kTcWStages) & 1);
+          mbar_wait(&bar_ops_full[o], (it / kTcOpsStages) & 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * kTcStageBytes + kTcRawBytes);
-          const uint32_t sb = sa + 3u * kTcASliceBytes;
+          const uint32_t sa = smem_u32(smem + kTcOpsOff + (size_t)o * kTcOpsBytes);
+          const uint32_t sb = smem_u32(smem + kTcWOff + (size_t)w * kTcWBytes);
 #pragma unroll
           for (int j = 0; j < kTcKC / 16; ++j) {
             const uint32_t ko = (uint32_t)j * 256u;     // two 16-byte K core matrices per MMA
@@ -342,38 +385,55 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
             const uint64_t dB0 = umma_desc(sb + ko, 128, 512);
             const uint64_t dB1 = umma_desc(sb + b_slice + ko, 128, 512);
             const uint64_t dB2 = umma_desc(sb + 2 * b_slice + ko, 128, 512);
-            const uint32_t first = (kc > 0 || j > 0) ? 1u : 0u;
-            umma_bf16(acc0, dA0, dB0, idesc, first);
-            umma_bf16(acc1, dA0, dB1, idesc, first);
+            const uint32_t acc = (kc > 0 || j > 0) ? 1u : 0u;
+            umma_bf16(acc0, dA0, dB0, idesc, acc);
+            umma_bf16(acc1, dA0, dB1, idesc, acc);
             umma_bf16(acc1, dA1, dB0, idesc, 1u);
             umma_bf16(acc1, dA0, dB2, idesc, 1u);
             umma_bf16(acc1, dA1, dB1, idesc, 1u);
             umma_bf16(acc1, dA2, dB0, idesc, 1u);
           }
-          umma_commit(&bar_empty[s]);                    // stage reusable once these MMAs have read it
+          umma_commit(&bar_ops_empty[o]);                // both operand slots reusable once these MMAs have read them
+          umma_commit(&bar_w_empty[w]);
         }
         umma_commit(&bar_acc_full[buf]);                 // accumulators of this tile complete
       }
     }
-  } else {
+  } else if (warp < 8) {
     // =================== epilogue (warps 4..7 <-> TMEM lanes 32*(warp-4) ..) ===================
     const int ew = warp - 4;
-    float* scratch = reinterpret_cast<float*>(smem + (size_t)kTcStages * kTcStageBytes) + ew * (32 * 33);
+    float* scratch = reinterpret_cast<float*>(smem + kTcEpiOff) + ew * (32 * 33);
     uint32_t tile_it = 0;
+    int Ea_next = row_exp(blockIdx.x, ew * 32 + lane);
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tile_it) {
       int b, mt, ci, nt;
       decode(t, b, mt, ci, nt);
       const TcLinBlock& B = a.blk[b];
       const int buf = tile_it & 1;
-      const int node_mine = mt * kTcBM + ew * 32 + lane;          // the row this thread holds in TMEM
-      int Ea = kTcZeroRow;
-      if (node_mine < a.n_nodes) Ea = __ldg(a.E + (size_t)node_mine * a.rows_per_node + B.row_base + ci);
+      const int Ea = Ea_next;                                       // the row this thread holds in TMEM
+      Ea_next = row_exp(t + gridDim.x, ew * 32 + lane);
       const float fa = (Ea == kTcZeroRow) ? 0.0f : exp2i(Ea - 7);
-      mbar_wait(&bar_acc_full[buf], (tile_it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 2 * B.NT);
+      const uint32_t lane_base = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 2 * kTcMaxNT)   /* fixed halves: tiles of different NT alternate */;
       const int col0 = nt * B.NT;
+      const int node0 = mt * kTcBM + ew * 32;
+      const int n_rows = min(32, a.n_nodes - node0);                // rows of this warp that exist (<= 0: none)
+      float* cbase = a.C + (size_t)node0 * a.ldc + B.c_off + (size_t)ci * B.c_cs + col0;
+      bool waited = false;
       for (int c = 0; c < B.NT; c += 32) {
+        const int cc = c + lane;                                    // this lane's column of the slab
+        const bool col_ok = cc < B.NT;
+        // C += ...: request the old values of the whole 32 x 32 slab first (32 independent coalesced loads)
+        float old[32];
+        if (a.accumulate) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) old[rr] = (col_ok && rr < n_rows) ? cbase[(size_t)rr * a.ldc + cc] : 0.0f;
+        }
+        const float fb = col_ok ? __ldg(B.fb + col0 + cc) : 0.0f;
+        if (!waited) {
+          mbar_wait(&bar_acc_full[buf], (tile_it >> 1) & 1);
+          tc_fence_after();
+          waited = true;
+        }
         uint32_t v0[32], v1[32];
         tmem_ld32(lane_base + (uint32_t)c, v0);
         tmem_ld32(lane_base + (uint32_t)(B.NT + c), v1);
@@ -382,19 +442,14 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         for (int j = 0; j < 32; ++j)
           scratch[lane * 33 + j] = (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * fa;
         __syncwarp();
-        const int cc = c + lane;                                    // this lane's column of the slab
-        const bool col_ok = cc < B.NT;
-        const float fb = col_ok ? __ldg(B.fb + col0 + cc) : 0.0f;
-        const int node0 = mt * kTcBM + ew * 32;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int node = node0 + rr;
-          if (node >= a.n_nodes) break;                             // uniform over the warp
-          if (col_ok) {
-            float* p = a.C + (size_t)node * a.ldc + B.c_off + (size_t)ci * B.c_cs + col0 + cc;
-            float v = scratch[rr * 33 + lane] * fb;
-            if (a.accumulate) v += *p;
-            *p = v;
+        if (col_ok) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < n_rows) {
+              float v = scratch[rr * 33 + lane] * fb;
+              if (a.accumulate) v += old[rr];
+              cbase[(size_t)rr * a.ldc + cc] = v;
+            }
           }
         }
         __syncwarp();

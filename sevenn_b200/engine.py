@@ -49,7 +49,10 @@ class S7bModelDesc(ctypes.Structure):
 EXPORTS = [
     's7b_last_error', 's7b_version', 's7b_set_option', 's7b_dense_linear', 's7b_engine_create', 's7b_engine_destroy',
     's7b_engine_set_atomic_virial', 's7b_tc_pack_weights', 's7b_gather_rows', 's7b_scatter_add_rows',
-    's7b_engine_set_interior',
+    's7b_engine_set_interior', 's7b_block_linear',
+    's7b_d3_create', 's7b_d3_destroy', 's7b_d3_set_params', 's7b_d3_set_damping', 's7b_d3_set_system', 's7b_d3_run_stage',
+    's7b_d3_buffer', 's7b_d3_results_host', 's7b_d3_compute_host', 'pair_init', 'pair_set_atom', 'pair_set_domain',
+    'pair_run_settings', 'pair_run_coeff', 'pair_run_compute', 'pair_get_energy', 'pair_get_force', 'pair_get_stress', 'pair_fin',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
     's7b_engine_buffer', 's7b_engine_compute_host', 's7b_engine_set_positions_host',
     's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_graph_stats', 's7b_engine_set_profiling',
@@ -80,6 +83,19 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_gather_rows.argtypes = [vp, i32, vp, i64, i32, vp, vp]
     lib.s7b_scatter_add_rows.argtypes = [vp, i32, vp, i64, i32, vp, vp]
     lib.s7b_engine_set_interior.argtypes = [vp, i32]
+    lib.s7b_block_linear.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
+    f64 = ctypes.c_double
+    lib.s7b_d3_create.argtypes = [ctypes.POINTER(vp)]
+    lib.s7b_d3_destroy.argtypes = [vp]
+    lib.s7b_d3_destroy.restype = None
+    lib.s7b_d3_set_params.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.s7b_d3_set_damping.argtypes = [vp, i32, f64, f64, f64, f64, f64, f64, f64, f64]
+    lib.s7b_d3_set_system.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.s7b_d3_run_stage.argtypes = [vp, i32, i32, i32, vp]
+    lib.s7b_d3_buffer.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(sz)]
+    lib.s7b_d3_buffer.restype = vp
+    lib.s7b_d3_results_host.argtypes = [vp, vp, vp, vp, vp]
+    lib.s7b_d3_compute_host.argtypes = [vp, vp, vp, vp, vp]
     lib.s7b_engine_set_param.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, vp, sz]
     lib.s7b_engine_set_graph.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp]
     lib.s7b_engine_run_stage.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
@@ -244,7 +260,9 @@ def prepare_params(spec: ModelSpec, arrays: Dict[str, np.ndarray], radial: str, 
     Lz = spec.layers[-1]
     r1 = f64(arrays['readout1']).reshape(Lz.out_muls[0], spec.readout_hidden) / math.sqrt(Lz.out_muls[0])
     r2 = f64(arrays['readout2']).reshape(spec.readout_hidden, 1) / math.sqrt(spec.readout_hidden)
-    out[('readout', -1)] = (r1 @ r2).ravel()
+    wr = (r1 @ r2).ravel()
+    out[('readout', -1)] = wr
+    out[('readout_lo', -1)] = wr - wr.astype(np.float32).astype(np.float64)     # residual of the fp32 rounding
     out[('scale', -1)] = f64(arrays['scale'])
     out[('shift', -1)] = f64(arrays['shift'])
     out[('bessel', -1)] = f64(arrays['bessel_coeffs'])

@@ -98,7 +98,7 @@ def test_library_exports_every_declared_symbol():
         import __graft_entry__
         __graft_entry__.build()
     header = open(os.path.join(ROOT, 'include', 'sevenn_b200.h')).read()
-    declared = re.findall(r'S7B_API\s+[\w\s\*]+?\b(s7b_\w+)\s*\(', header)
+    declared = re.findall(r'S7B_API\s+[\w\s\*]+?\b((?:s7b|pair)_\w+)\s*\(', header)
     assert len(declared) >= 16
     lib = ctypes.CDLL(lib_path)
     for sym in declared:
