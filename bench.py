@@ -488,6 +488,133 @@ def distributed_parity(runner, eng, meta, arrays, pos, cell, species_all, local_
     return out
 
 
+def run_nacl_d3(args):
+    """BASELINE configs[4]: SevenNet-0 + D3 dispersion on a rocksalt NaCl cell (25x25x10 = 50 000 atoms by
+    default), N GPUs: the network by spatial bricks + NCCL ghost exchange, the D3 correction by atom
+    decomposition with replicated positions (three small all-gathers).  One step = both, summed."""
+    import torch
+    import torch.distributed as dist
+    from sevenn_b200.checkpoint import load_weights
+    from sevenn_b200.d3 import D3Engine, distributed_d3
+    from sevenn_b200.engine import B200Engine
+    from sevenn_b200.neighbors import build_graph, rocksalt_nacl
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=300))
+    meta, arrays = load_weights(os.path.join(ROOT, 'weights', 'sevennet_0.npz'))
+    tm = {int(k): int(v) for k, v in meta['type_map'].items()}
+    cells = (25, 25, 10) if args.cells is None else tuple(args.cells)
+    pos, cell, z = rocksalt_nacl(*cells, sigma=0.05, seed=0)
+    n_atoms = len(z)
+    species = np.array([tm[int(a)] for a in z], dtype=np.int32)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    eng = B200Engine(meta, arrays, radial=args.radial, device=local_rank)
+    d3 = D3Engine('damp_bj', 'pbe', device=local_rank)
+    if world == 1:
+        ei, ev = build_graph(pos, cell, True, 5.0)
+        n_edges = ei.shape[1]
+        eng.set_graph(species, ei, ev)
+
+        def step():
+            eng.compute()
+            d3.set_system(z, pos, cell)
+            for st in (1, 2, 3):
+                d3.run_stage(st)
+    else:
+        from sevenn_b200.parallel import DistributedRunner, brick_decompose
+        part = brick_decompose(pos, cell, species, GRIDS[args.gpus], rank, 5.0)
+        runner = DistributedRunner(eng, part)
+        t = torch.tensor([part['edge_index'].shape[1]], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        n_edges = int(t.item())
+
+        def step():
+            runner.compute()
+            distributed_d3(d3, z, pos, cell)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total = 0.0
+    t_net = t_d3 = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        if world > 1:
+            dist.barrier()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        if world == 1:
+            eng.compute()
+        else:
+            runner.compute()
+        b.record()
+        if world == 1:
+            d3.set_system(z, pos, cell)
+            for st in (1, 2, 3):
+                d3.run_stage(st)
+            e_d3, f_d3, s_d3 = d3.results()
+        else:
+            e_d3, f_d3, s_d3 = distributed_d3(d3, z, pos, cell)
+        c.record()
+        torch.cuda.synchronize()
+        total += a.elapsed_time(c)
+        t_net += a.elapsed_time(b)
+        t_d3 += b.elapsed_time(c)
+    clocks = sampler.stop()
+    tt = torch.tensor([total, t_net, t_d3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total, t_net, t_d3 = (float(v) for v in tt.cpu())
+    e_net = float((eng.buffer('energy', dtype='f8')).cpu()[0])
+    parity = None
+    if world > 1:      # rank 0: the same system on one GPU, network and D3
+        f_all = torch.zeros(n_atoms, 3, dtype=torch.float32, device=dev)
+        r = runner.results()
+        gids = torch.as_tensor(np.asarray(r['global_ids']), dtype=torch.long, device=dev)
+        f_all[gids] = r['forces']
+        dist.all_reduce(f_all)
+        if rank == 0:
+            ei, ev = build_graph(pos, cell, True, 5.0)
+            single = B200Engine(meta, arrays, radial=args.radial, device=local_rank)
+            single.set_graph(species, ei, ev)
+            single.compute()
+            torch.cuda.synchronize()
+            rs = single.results()
+            e1, f1, _ = D3Engine('damp_bj', 'pbe', device=local_rank).compute(z, pos, cell)
+            tolE, tolF = parity_tolerance(n_atoms)
+            parity = {'against': 'the same system on ONE GPU (rank 0): SevenNet-0 and D3 separately',
+                      'net_dE_eV': e_net - float(rs['energy'].cpu()[0]), 'net_max_dF': float((f_all - rs['forces']).abs().max()),
+                      'd3_dE_eV': e_d3 - e1, 'd3_max_dF': float(np.abs(f_d3 - f1).max()), 'tol_dE_eV': tolE, 'tol_dF_eV_per_A': tolF}
+            parity['ok'] = bool(abs(parity['net_dE_eV']) <= tolE and parity['net_max_dF'] <= tolF
+                                and abs(parity['d3_dE_eV']) <= tolE and parity['d3_max_dF'] <= tolF)
+        dist.barrier()
+    if rank == 0:
+        ms = total / args.steps
+        line = {'metric': METRIC, 'value': n_atoms / (ms * 1e-3), 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f32 (network), f32 pair terms / f64 sums (D3)', 'data': 'synthetic',
+                'config': {'workload': f'SevenNet-0 + D3(BJ, pbe, 9000/1600 bohr^2) energy+forces per MD step, rocksalt NaCl '
+                                       f'{cells[0]}x{cells[1]}x{cells[2]} cells = {n_atoms} atoms, {n_edges} network edges',
+                           'parallelism': 'single GPU' if world == 1 else f'network: spatial bricks {GRIDS[args.gpus]} + NCCL ghost exchange; '
+                                          f'D3: atom decomposition, replicated positions, 3 all-gathers',
+                           'l2': 'flushed with a 256 MiB write between timed steps',
+                           'note': 'the reference D3 is single-GPU, O(N^2) and capped at 46 340 atoms; this cell exceeds it'},
+                'ms_network': t_net / args.steps, 'ms_d3': t_d3 / args.steps, 'energy_network_eV': e_net, 'energy_d3_eV': e_d3,
+                'clocks': clocks, 'parity': parity}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def roofline_from_profile(eng, prof, n_edges, n_dst):
     """Roofline of the dominant kernel from the engine's CUDA-event profile.
     The convolution kernels keep x (23 MB) and the radial tables (23 MB/layer) L2-resident, so their
@@ -585,11 +712,15 @@ def main():
     ap.add_argument('--parity', default='cuda', choices=['cuda', 'cpu', 'off'],
                     help='where the fp64 oracle of the one-off parity check runs (it is the checker, never timed)')
     ap.add_argument('--no-extras', action='store_true', help='skip the l3i5 / gpu_standin legs of the N = 1 line')
+    ap.add_argument('--workload', default='si', choices=['si', 'nacl_d3'],
+                    help="'si': the headline benchmark (BASELINE configs[1]/[3]); 'nacl_d3': configs[4], SevenNet-0 + D3 on NaCl")
     args = ap.parse_args()
     if args.gpus not in CELLS:
         raise SystemExit('--gpus must be 1, 2, 4 or 8')
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'nacl_d3':
+        run_nacl_d3(args)
     else:
         run_engine(args)
 

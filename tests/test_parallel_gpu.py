@@ -89,3 +89,46 @@ def test_multi_gpu_matches_oracle(world, grid, model):
     assert np.allclose(forces, ref['forces'].numpy(), atol=5e-5)
     assert np.allclose(forces_h, forces, atol=5e-6)
     assert np.allclose(ae, ref['atomic_energy'].numpy(), atol=2e-5)
+
+
+def _d3_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from sevenn_b200.d3 import D3Engine, distributed_d3
+    from sevenn_b200.neighbors import rocksalt_nacl
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        pos, cell, z = rocksalt_nacl(3, 3, 2, sigma=0.05, seed=2)
+        e, f, s = distributed_d3(D3Engine(device=rank), z, pos, cell)
+        q.put((rank, e, f, s))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_multi_gpu_d3_matches_single_gpu(world):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
+    from sevenn_b200.d3 import D3Engine
+    from sevenn_b200.neighbors import rocksalt_nacl
+    pos, cell, z = rocksalt_nacl(3, 3, 2, sigma=0.05, seed=2)
+    e1, f1, s1 = D3Engine(device=0).compute(z, pos, cell)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_d3_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, e, f, s in res:
+        assert abs(e - e1) < 1e-9 * abs(e1)
+        assert np.abs(f - f1).max() < 1e-10
+        assert np.abs(s - s1).max() < 1e-9 * np.abs(s1).max()
