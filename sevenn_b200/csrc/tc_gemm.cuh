@@ -77,16 +77,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive that carries a data dependency on `dep`: the arrival cannot issue before the value is in its
-// register, i.e. before the shared-memory loads that produced it have returned (releasing a slot that was
-// read with plain loads: the refill by the TMA engine must not overtake them)
+// arrive that carries a REAL data dependency on `dep`: the arrival is predicated on a comparison of the
+// value with a bit pattern no fp32 addition can produce, so neither nvcc nor ptxas can drop the dependency
+// (a dead `mov` was dropped: the SASS then issued SYNCS.ARRIVE right behind the still outstanding loads and
+// the TMA refill overtook them).  The warp therefore waits for the shared-memory loads that produced
+// `dep` before it releases the slot they read.
 __device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, float dep) {
   asm volatile(
       "{\n"
-      ".reg .b32 t;\n"
-      "mov.b32 t, %1;\n"
-      "mbarrier.arrive.shared::cta.b64 _, [%0];\n"
-      "}\n" ::"r"(smem_u32(bar)), "f"(dep) : "memory");
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %1, 0x7fc12345;\n"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(__float_as_uint(dep)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -210,6 +212,25 @@ struct TcLinArgs {
 };
 struct TcMaps { CUtensorMap m[kMaxL]; };   // per block: A viewed as (k, component, node), fp32
 
+// explicit shared-space accesses (the ring pointers are computed from an aligned base, which makes the compiler
+// fall back to generic LD/ST otherwise)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -315,18 +336,17 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
       for (int kc = 0; kc < n_kc; ++kc, ++it) {
         const int s = it % kTcRawStages, o = it % kTcOpsStages;
         mbar_wait(&bar_raw_full[s], (it / kTcRawStages) & 1);
-        const uint8_t* raw = smem + kTcRawOff + (size_t)s * kTcRawBytes + (size_t)r * 128;
+        const uint32_t raw = smem_u32(smem + kTcRawOff + (size_t)s * kTcRawBytes + (size_t)r * 128);
         float4 v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(raw + (((uint32_t)q ^ swz) << 4));
+        for (int q = 0; q < 8; ++q) v[q] = lds128(raw + (((uint32_t)q ^ swz) << 4));
         float dep = v[0].x;                             // touches every load: all eight have returned
 #pragma unroll
         for (int q = 1; q < 8; ++q) dep += v[q].x;
         mbar_arrive_after(&bar_raw_empty[s], dep);      // the raw chunk is in registers: its slot can be refilled
         mbar_wait(&bar_ops_empty[o], ((it / kTcOpsStages) & 1) ^ 1);
-        uint8_t* a0 = smem + kTcOpsOff + (size_t)o * kTcOpsBytes;
-        uint8_t* a1 = a0 + kTcASliceBytes;
-        uint8_t* a2 = a1 + kTcASliceBytes;
+        const uint32_t a0 = smem_u32(smem + kTcOpsOff + (size_t)o * kTcOpsBytes);
+        const uint32_t a1 = a0 + kTcASliceBytes, a2 = a1 + kTcASliceBytes;
 #pragma unroll
         for (int kq = 0; kq < 4; ++kq) {                // 8 consecutive k = one 16-byte core-matrix row
           const float x[8] = {v[2 * kq].x, v[2 * kq].y, v[2 * kq].z, v[2 * kq].w,
@@ -345,9 +365,9 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
             s2[j] = q2 * 1.52587890625e-05f;
           }
           const uint32_t off = row_off + (uint32_t)kq * 128u;
-          *reinterpret_cast<uint4*>(a0 + off) = make_uint4(pack_bf16(s0[0], s0[1]), pack_bf16(s0[2], s0[3]), pack_bf16(s0[4], s0[5]), pack_bf16(s0[6], s0[7]));
-          *reinterpret_cast<uint4*>(a1 + off) = make_uint4(pack_bf16(s1[0], s1[1]), pack_bf16(s1[2], s1[3]), pack_bf16(s1[4], s1[5]), pack_bf16(s1[6], s1[7]));
-          *reinterpret_cast<uint4*>(a2 + off) = make_uint4(pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
+          sts128(a0 + off, pack_bf16(s0[0], s0[1]), pack_bf16(s0[2], s0[3]), pack_bf16(s0[4], s0[5]), pack_bf16(s0[6], s0[7]));
+          sts128(a1 + off, pack_bf16(s1[0], s1[1]), pack_bf16(s1[2], s1[3]), pack_bf16(s1[4], s1[5]), pack_bf16(s1[6], s1[7]));
+          sts128(a2 + off, pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
         }
         fence_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         mbar_arrive(&bar_ops_full[o]);
@@ -402,7 +422,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
   } else if (warp < 8) {
     // =================== epilogue (warps 4..7 <-> TMEM lanes 32*(warp-4) ..) ===================
     const int ew = warp - 4;
-    float* scratch = reinterpret_cast<float*>(smem + kTcEpiOff) + ew * (32 * 33);
+    const uint32_t scratch = smem_u32(smem + kTcEpiOff) + (uint32_t)ew * (32 * 33 * 4);
     uint32_t tile_it = 0;
     int Ea_next = row_exp(blockIdx.x, ew * 32 + lane);
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tile_it) {
@@ -440,13 +460,13 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          scratch[lane * 33 + j] = (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * fa;
+          sts32(scratch + (uint32_t)(lane * 33 + j) * 4, (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * fa);
         __syncwarp();
         if (col_ok) {
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
             if (rr < n_rows) {
-              float v = scratch[rr * 33 + lane] * fb;
+              float v = lds32(scratch + (uint32_t)(rr * 33 + lane) * 4) * fb;
               if (a.accumulate) v += old[rr];
               cbase[(size_t)rr * a.ldc + cc] = v;
             }
