@@ -186,6 +186,14 @@ S7B_API int s7b_engine_compute_positions_host(S7bEngine* eng, int32_t n_atoms, c
                                               float* forces, double* virial, int64_t* n_edges_out,
                                               void* stream);
 
+/* Multi-GPU front-end: neighbour rows of a subset of centre atoms (a rank's own atoms, `centres` = indices into
+ * the n_atoms atoms) against ALL atoms, built on the device with the same semantics as above.  Does not touch
+ * the engine's graph: read "nl_rowptr" [n_centres+1], "nl_src" [E] (indices into the n_atoms atoms), "nl_vec"
+ * [E,3] with s7b_engine_buffer.  Replaces the per-step ghost / edge build of pair_e3gnn_parallel.cpp:194-340. */
+S7B_API int s7b_engine_neighbor_rows_host(S7bEngine* eng, int32_t n_atoms, const int32_t* species, const double* positions,
+                                          const double* cell9, const int32_t* pbc3, int32_t n_centres,
+                                          const int32_t* centres, int64_t* n_edges_out, void* stream);
+
 /* Per-kernel timing with CUDA events recorded on the launching stream around every kernel (or
  * kernel group) of the stage sequence; labels like "conv_bwd.t2.l1".  Enable, run steps, then read. */
 S7B_API int s7b_engine_set_profiling(S7bEngine* eng, int enable);

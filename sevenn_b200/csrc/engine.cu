@@ -176,7 +176,9 @@ struct S7bEngine {
   // host staging for compute_host
   DevBuf hs_species, hs_rowptr, hs_src, hs_vec, hs_centre, hs_flag;
   // device neighbour list (positions -> CSR)
-  DevBuf nl_pos, nl_wrapped, nl_key, nl_key_sorted, nl_idx, nl_idx_sorted, nl_bin_start, nl_count, nl_tmp;
+  DevBuf nl_pos, nl_wrapped, nl_key, nl_key_sorted, nl_idx, nl_idx_sorted, nl_bin_start, nl_count, nl_tmp, nl_centres;
+  int nl_n_centres = 0;
+  int64_t nl_n_edges = 0;
   Profiler prof;
   // side streams: the per-l1 convolution kernels of one layer are independent (disjoint outputs) and
   // stress different units (l1 = 0: L1/L2 latency, l1 >= 1: FP32 pipe), so they are co-scheduled
@@ -822,7 +824,7 @@ void s7b_engine_destroy(S7bEngine* e) {
                     &e->mid, &e->h, &e->dh, &e->dg, &e->dx, &e->dwbuf, &e->tmpA, &e->tmpB, &e->energy,
                     &e->atomic_energy, &e->forces, &e->virial, &e->atomic_virial, &e->hs_species, &e->hs_rowptr, &e->hs_src,
                     &e->hs_vec, &e->hs_centre, &e->hs_flag, &e->nl_pos, &e->nl_wrapped, &e->nl_key, &e->nl_key_sorted,
-                    &e->nl_idx, &e->nl_idx_sorted, &e->nl_bin_start, &e->nl_count, &e->nl_tmp};
+                    &e->nl_idx, &e->nl_idx_sorted, &e->nl_bin_start, &e->nl_count, &e->nl_tmp, &e->nl_centres};
   for (DevBuf* b : bufs) b->release();
   for (auto* v : {&e->x, &e->g, &e->wbuf, &e->z1, &e->z2, &e->h1, &e->h2})
     for (auto& b : *v) b.release();
@@ -1349,6 +1351,9 @@ void* s7b_engine_buffer(S7bEngine* e, const char* name, int layer, size_t* numel
   else if (nm == "graph_rowptr") { p = (void*)e->d_rowptr; n = (size_t)e->n_local + 1; }
   else if (nm == "graph_src") { p = (void*)e->d_src; n = (size_t)e->n_edges; }
   else if (nm == "graph_edge_vec") { p = (void*)e->d_edge_vec; n = (size_t)e->n_edges * 3; }
+  else if (nm == "nl_rowptr") { p = e->hs_rowptr.p; n = (size_t)e->nl_n_centres + 1; }
+  else if (nm == "nl_src") { p = e->hs_src.p; n = (size_t)e->nl_n_edges; }
+  else if (nm == "nl_vec") { p = e->hs_vec.p; n = (size_t)e->nl_n_edges * 3; }
   else if (nm == "edge_len") { p = e->rlen.p; n = (size_t)e->n_edges; }
   else if (nm == "edge_emb") { p = e->emb.p; n = (size_t)e->n_edges * e->desc.n_basis; }
   else if (nm == "dY_acc") { p = e->dY_acc.p; n = (size_t)e->n_edges * e->ny_stride; }
@@ -1411,10 +1416,15 @@ static int invert3(const double* m, double* inv) {
   return 0;
 }
 
-int s7b_engine_set_positions_host(S7bEngine* e, int32_t n_atoms, const int32_t* species, const double* positions,
-                                  const double* cell9, const int32_t* pbc3, void* stream) {
+// Neighbour list of `n_centres` centre atoms (centres == nullptr: all n_atoms atoms) against all atoms;
+// leaves species / rowptr [n_centres + 1] / src (indices into the n_atoms atoms) / edge_vec in the hs_* buffers.
+static int build_neighbor_list(S7bEngine* e, int32_t n_atoms, const int32_t* species, const double* positions,
+                               const double* cell9, const int32_t* pbc3, int32_t n_centres, const int32_t* centres_host,
+                               int64_t* n_edges_out, void* stream) {
   if (!e) return fail("null engine");
   if (n_atoms < 0 || (n_atoms > 0 && (!species || !positions))) return fail("bad arguments");
+  if (centres_host == nullptr) n_centres = n_atoms;
+  if (n_centres < 0 || n_centres > n_atoms) return fail("bad centre count");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   NLGrid g;
   memset(&g, 0, sizeof(g));
@@ -1472,8 +1482,14 @@ int s7b_engine_set_positions_host(S7bEngine* e, int32_t n_atoms, const int32_t* 
   rc |= e->nl_idx_sorted.ensure(N * sizeof(int));
   rc |= e->nl_bin_start.ensure(((size_t)nbins + 1) * sizeof(int));
   rc |= e->nl_count.ensure((N + 1) * sizeof(int));
+  rc |= e->nl_centres.ensure(N * sizeof(int));
   if (rc) return fail("cudaMalloc failed for the neighbour list");
   int64_t n_edges = 0;
+  const int* d_centres = nullptr;
+  if (centres_host != nullptr && n_centres > 0) {
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->nl_centres.p, centres_host, (size_t)n_centres * sizeof(int), cudaMemcpyHostToDevice, st));
+    d_centres = e->nl_centres.as<int>();
+  }
   if (n_atoms > 0) {
     S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_species.p, species, (size_t)n_atoms * sizeof(int), cudaMemcpyHostToDevice, st));
     S7B_CUDA_CHECK(cudaMemcpyAsync(e->nl_pos.p, positions, (size_t)n_atoms * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1490,25 +1506,47 @@ int s7b_engine_set_positions_host(S7bEngine* e, int32_t n_atoms, const int32_t* 
     nl_bin_start_kernel<<<(n_atoms + 1 + 255) / 256, 256, 0, st>>>(e->nl_key_sorted.as<int>(), n_atoms, (int)nbins, e->nl_bin_start.as<int>());
     S7B_LAUNCH_CHECK();
     S7B_CUDA_CHECK(cudaMemsetAsync(e->nl_count.p, 0, ((size_t)n_atoms + 1) * sizeof(int), st));
-    nl_pairs_kernel<false><<<grd, blk, 0, st>>>(g, e->nl_wrapped.as<double>(), e->nl_key.as<int>(), e->nl_idx_sorted.as<int>(), e->nl_bin_start.as<int>(), n_atoms, e->nl_count.as<int>(), nullptr, nullptr, nullptr);
+    const int grd_c = std::max(1, (n_centres + blk - 1) / blk);
+    nl_pairs_kernel<false><<<grd_c, blk, 0, st>>>(g, e->nl_wrapped.as<double>(), e->nl_key.as<int>(), e->nl_idx_sorted.as<int>(), e->nl_bin_start.as<int>(), n_centres, e->nl_count.as<int>(), nullptr, nullptr, nullptr, d_centres);
     S7B_LAUNCH_CHECK();
     tmp = e->nl_tmp.bytes;
-    S7B_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(e->nl_tmp.p, tmp, e->nl_count.as<int>(), e->hs_rowptr.as<int>(), n_atoms + 1, st));
+    S7B_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(e->nl_tmp.p, tmp, e->nl_count.as<int>(), e->hs_rowptr.as<int>(), n_centres + 1, st));
     ++g_launches;
     int total = 0;
-    S7B_CUDA_CHECK(cudaMemcpyAsync(&total, e->hs_rowptr.as<int>() + n_atoms, sizeof(int), cudaMemcpyDeviceToHost, st));
+    S7B_CUDA_CHECK(cudaMemcpyAsync(&total, e->hs_rowptr.as<int>() + n_centres, sizeof(int), cudaMemcpyDeviceToHost, st));
     S7B_CUDA_CHECK(cudaStreamSynchronize(st));
     n_edges = total;
     const size_t E = (size_t)std::max<int64_t>(n_edges, 1);
     if (e->hs_src.ensure(E * sizeof(int)) || e->hs_vec.ensure(E * 3 * sizeof(float))) return fail("cudaMalloc failed for the edge list");
     if (n_edges > 0) {
-      nl_pairs_kernel<true><<<grd, blk, 0, st>>>(g, e->nl_wrapped.as<double>(), e->nl_key.as<int>(), e->nl_idx_sorted.as<int>(), e->nl_bin_start.as<int>(), n_atoms, nullptr, e->hs_rowptr.as<int>(), e->hs_src.as<int>(), e->hs_vec.as<float>());
+      nl_pairs_kernel<true><<<grd_c, blk, 0, st>>>(g, e->nl_wrapped.as<double>(), e->nl_key.as<int>(), e->nl_idx_sorted.as<int>(), e->nl_bin_start.as<int>(), n_centres, nullptr, e->hs_rowptr.as<int>(), e->hs_src.as<int>(), e->hs_vec.as<float>(), d_centres);
       S7B_LAUNCH_CHECK();
     }
   } else {
     S7B_CUDA_CHECK(cudaMemsetAsync(e->hs_rowptr.p, 0, sizeof(int), st));
   }
+  e->nl_n_centres = n_centres;
+  e->nl_n_edges = n_edges;
+  if (n_edges_out) *n_edges_out = n_edges;
+  return 0;
+}
+
+int s7b_engine_set_positions_host(S7bEngine* e, int32_t n_atoms, const int32_t* species, const double* positions,
+                                  const double* cell9, const int32_t* pbc3, void* stream) {
+  int64_t n_edges = 0;
+  if (build_neighbor_list(e, n_atoms, species, positions, cell9, pbc3, n_atoms, nullptr, &n_edges, stream)) return 1;
   return s7b_engine_set_graph(e, n_atoms, n_atoms, n_edges, e->hs_species.as<int>(), e->hs_rowptr.as<int>(), e->hs_src.as<int>(), e->hs_vec.as<float>(), stream);
+}
+
+// Multi-GPU front-end (pair_e3gnn_parallel.cpp:194-340): the rows of a SUBSET of centre atoms
+// (a rank's own atoms) against all atoms of the system, built on the device.  Nothing becomes the engine's
+// graph; the caller reads "nl_rowptr" [n_centres + 1], "nl_src" [E] (indices into the n_atoms atoms) and
+// "nl_vec" [E, 3] with s7b_engine_buffer, maps neighbours to local / ghost rows and calls s7b_engine_set_graph.
+int s7b_engine_neighbor_rows_host(S7bEngine* e, int32_t n_atoms, const int32_t* species, const double* positions,
+                                  const double* cell9, const int32_t* pbc3, int32_t n_centres, const int32_t* centres,
+                                  int64_t* n_edges_out, void* stream) {
+  if (!centres && n_centres > 0) return fail("null centre list");
+  return build_neighbor_list(e, n_atoms, species, positions, cell9, pbc3, n_centres, centres, n_edges_out, stream);
 }
 
 int s7b_engine_compute_positions_host(S7bEngine* e, int32_t n_atoms, const int32_t* species, const double* positions,

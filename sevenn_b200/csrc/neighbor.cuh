@@ -66,19 +66,22 @@ static __global__ void nl_bin_start_kernel(const int* __restrict__ key_sorted, i
   for (int b = prev + 1; b <= cur; ++b) bin_start[b] = s;
 }
 
-// One thread per centre atom i (original numbering).  FILL = false: count[i] = neighbours;
-// FILL = true: write src / edge_vec at rowptr[i] + running offset.
+// One thread per centre atom (centre c = centres[tid], or tid itself when centres == nullptr; original
+// numbering).  FILL = false: count[tid] = neighbours; FILL = true: write src / edge_vec at rowptr[tid] +
+// running offset.  A centre subset is what a rank of the multi-GPU runner asks for: the rows of its own atoms.
 template <bool FILL>
 __global__ void nl_pairs_kernel(const NLGrid g, const double* __restrict__ wrapped, const int* __restrict__ key,
                                 const int* __restrict__ idx_sorted, const int* __restrict__ bin_start, int n,
                                 int* __restrict__ count, const int* __restrict__ rowptr,
-                                int* __restrict__ src, float* __restrict__ edge_vec) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                                int* __restrict__ src, float* __restrict__ edge_vec,
+                                const int* __restrict__ centres = nullptr) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n) return;
+  const int i = centres != nullptr ? centres[tid] : tid;
   const double xi = wrapped[3 * i], yi = wrapped[3 * i + 1], zi = wrapped[3 * i + 2];
   const int k = key[i];
   const int b2 = k % g.nb[2], b1 = (k / g.nb[2]) % g.nb[1], b0 = k / (g.nb[2] * g.nb[1]);
-  int out = FILL ? rowptr[i] : 0;
+  int out = FILL ? rowptr[tid] : 0;
   for (int d0 = -g.R[0]; d0 <= g.R[0]; ++d0) {
     int q0 = b0 + d0, s0 = 0;
     if (g.pbc[0]) { s0 = (q0 >= 0) ? q0 / g.nb[0] : -((-q0 + g.nb[0] - 1) / g.nb[0]); q0 -= s0 * g.nb[0]; }
@@ -113,7 +116,7 @@ __global__ void nl_pairs_kernel(const NLGrid g, const double* __restrict__ wrapp
       }
     }
   }
-  if (!FILL) count[i] = out;
+  if (!FILL) count[tid] = out;
 }
 
 }  // namespace s7b

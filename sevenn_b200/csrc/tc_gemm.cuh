@@ -41,7 +41,8 @@ namespace s7b {
 constexpr int kTcBM = 128;          // rows (nodes) per tile
 constexpr int kTcKC = 32;           // K elements per pipeline stage
 constexpr int kTcMaxNT = 128;       // columns per tile (two accumulators x two buffers = 512 TMEM columns)
-constexpr int kTcThreads = 352;     // 4 transform + 4 epilogue warps, A producer, MMA issuer, W producer
+constexpr int kTcThreads = 480;     // 8 transform + 4 epilogue warps, A producer, MMA issuer, W producer
+constexpr int kTcXformThreads = 256; // two threads per row of a chunk (16 of its 32 k each)
 constexpr int kTcRawBytes = kTcBM * kTcKC * 4;            // 16 KB raw fp32 A chunk
 constexpr int kTcASliceBytes = kTcBM * kTcKC * 2;         // 8 KB per bf16 slice
 constexpr int kTcBSliceBytes = kTcMaxNT * kTcKC * 2;      // 8 KB per bf16 slice (NT = 128)
@@ -248,13 +249,13 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 9) {
+  if (warp == 13) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < kTcRawStages; ++s) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], 128); }
-    for (int s = 0; s < kTcOpsStages; ++s) { mbar_init(&bar_ops_full[s], 128); mbar_init(&bar_ops_empty[s], 1); }
+    for (int s = 0; s < kTcRawStages; ++s) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], kTcXformThreads); }
+    for (int s = 0; s < kTcOpsStages; ++s) { mbar_init(&bar_ops_full[s], kTcXformThreads); mbar_init(&bar_ops_empty[s], 1); }
     for (int s = 0; s < kTcWStages; ++s) { mbar_init(&bar_w_full[s], 1); mbar_init(&bar_w_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -283,7 +284,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
     return node < a.n_nodes ? __ldg(a.E + (size_t)node * a.rows_per_node + a.blk[b].row_base + ci) : kTcZeroRow;
   };
 
-  if (warp == 8) {
+  if (warp == 12) {
     // =================== TMA producer, A: raw fp32 chunks ===================
     if (lane == 0) {
       uint32_t it = 0;
@@ -299,7 +300,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 14) {
     // =================== TMA producer, W: pre-sliced bf16 chunks ===================
     if (lane == 0) {
       uint32_t it = 0;
@@ -318,12 +319,13 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         }
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 8) {
     // =================== transform: raw fp32 row -> three bf16 slices ===================
-    const int r = tid;                                  // row of the tile
+    // thread (r, h): row r of the tile, k = 16 h .. 16 h + 15 of the chunk; packed fp32 arithmetic (FFMA2 ...)
+    const int r = tid & 127, h = tid >> 7;
     const uint32_t swz = a.swizzle ? (uint32_t)(r & 7) : 0u;
     const uint32_t row_off = (uint32_t)((r & 7) * 16 + (r >> 3) * 512);
-    const float M = 12582912.0f;                        // 1.5 * 2^23: (x + M) - M = rint(x)
+    const V2 M2 = splat2(12582912.0f), nM2 = splat2(-12582912.0f);     // 1.5 * 2^23: (x + M) - M = rint(x)
     uint32_t it = 0;
     int Ea_next = row_exp(blockIdx.x, r);
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
@@ -337,43 +339,42 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         const int s = it % kTcRawStages, o = it % kTcOpsStages;
         mbar_wait(&bar_raw_full[s], (it / kTcRawStages) & 1);
         const uint32_t raw = smem_u32(smem + kTcRawOff + (size_t)s * kTcRawBytes + (size_t)r * 128);
-        float4 v[8];
+        float4 v[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = lds128(raw + (((uint32_t)q ^ swz) << 4));
-        float dep = v[0].x;                             // touches every load: all eight have returned
-#pragma unroll
-        for (int q = 1; q < 8; ++q) dep += v[q].x;
-        mbar_arrive_after(&bar_raw_empty[s], dep);      // the raw chunk is in registers: its slot can be refilled
+        for (int q = 0; q < 4; ++q) v[q] = lds128(raw + (((uint32_t)(4 * h + q) ^ swz) << 4));
+        const float dep = (v[0].x + v[1].x) + (v[2].x + v[3].x);   // touches every load: all four have returned
+        mbar_arrive_after(&bar_raw_empty[s], dep);                  // the raw chunk is in registers: its slot can be refilled
         mbar_wait(&bar_ops_empty[o], ((it / kTcOpsStages) & 1) ^ 1);
         const uint32_t a0 = smem_u32(smem + kTcOpsOff + (size_t)o * kTcOpsBytes);
         const uint32_t a1 = a0 + kTcASliceBytes, a2 = a1 + kTcASliceBytes;
 #pragma unroll
-        for (int kq = 0; kq < 4; ++kq) {                // 8 consecutive k = one 16-byte core-matrix row
-          const float x[8] = {v[2 * kq].x, v[2 * kq].y, v[2 * kq].z, v[2 * kq].w,
-                              v[2 * kq + 1].x, v[2 * kq + 1].y, v[2 * kq + 1].z, v[2 * kq + 1].w};
-          float s0[8], s1[8], s2[8];
+        for (int kk = 0; kk < 2; ++kk) {                // 8 consecutive k = one 16-byte core-matrix row
+          const V2 x[4] = {make_float2(v[2 * kk].x, v[2 * kk].y), make_float2(v[2 * kk].z, v[2 * kk].w),
+                           make_float2(v[2 * kk + 1].x, v[2 * kk + 1].y), make_float2(v[2 * kk + 1].z, v[2 * kk + 1].w)};
+          uint32_t p0[4], p1[4], p2[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float tt = x[j] * sc;
-            const float q0 = __fadd_rn(__fmaf_rn(tt, 1.52587890625e-05f, M), -M);        // rint(t / 2^16)
-            const float r1 = __fmaf_rn(q0, -65536.0f, tt);                               // exact
-            const float q1 = __fadd_rn(__fmaf_rn(r1, 0.00390625f, M), -M);               // rint(r1 / 2^8)
-            const float r2 = __fmaf_rn(q1, -256.0f, r1);                                 // exact
-            const float q2 = __fadd_rn(__fadd_rn(r2, M), -M);                            // rint(r2)
-            s0[j] = q0;
-            s1[j] = q1 * 0.00390625f;
-            s2[j] = q2 * 1.52587890625e-05f;
+          for (int j = 0; j < 4; ++j) {
+            const V2 tt = mul_(x[j], sc);
+            const V2 q0 = add_(fma_(tt, splat2(1.52587890625e-05f), M2), nM2);        // rint(t / 2^16)
+            const V2 r1 = fma_(q0, splat2(-65536.0f), tt);                            // exact
+            const V2 q1 = add_(fma_(r1, splat2(0.00390625f), M2), nM2);               // rint(r1 / 2^8)
+            const V2 r2 = fma_(q1, splat2(-256.0f), r1);                              // exact
+            const V2 q2 = add_(add_(r2, M2), nM2);                                    // rint(r2)
+            const V2 s1 = mul_(q1, 0.00390625f), s2 = mul_(q2, 1.52587890625e-05f);
+            p0[j] = pack_bf16(q0.x, q0.y);
+            p1[j] = pack_bf16(s1.x, s1.y);
+            p2[j] = pack_bf16(s2.x, s2.y);
           }
-          const uint32_t off = row_off + (uint32_t)kq * 128u;
-          sts128(a0 + off, pack_bf16(s0[0], s0[1]), pack_bf16(s0[2], s0[3]), pack_bf16(s0[4], s0[5]), pack_bf16(s0[6], s0[7]));
-          sts128(a1 + off, pack_bf16(s1[0], s1[1]), pack_bf16(s1[2], s1[3]), pack_bf16(s1[4], s1[5]), pack_bf16(s1[6], s1[7]));
-          sts128(a2 + off, pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]), pack_bf16(s2[4], s2[5]), pack_bf16(s2[6], s2[7]));
+          const uint32_t off = row_off + (uint32_t)(2 * h + kk) * 128u;
+          sts128(a0 + off, p0[0], p0[1], p0[2], p0[3]);
+          sts128(a1 + off, p1[0], p1[1], p1[2], p1[3]);
+          sts128(a2 + off, p2[0], p2[1], p2[2], p2[3]);
         }
         fence_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         mbar_arrive(&bar_ops_full[o]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // =================== MMA issuer ===================
     if (lane == 0) {
       uint32_t it = 0, tile_it = 0;
@@ -419,9 +420,9 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         umma_commit(&bar_acc_full[buf]);                 // accumulators of this tile complete
       }
     }
-  } else if (warp < 8) {
-    // =================== epilogue (warps 4..7 <-> TMEM lanes 32*(warp-4) ..) ===================
-    const int ew = warp - 4;
+  } else if (warp < 12) {
+    // =================== epilogue (warps 8..11 <-> TMEM lanes 32*(warp-8) ..) ===================
+    const int ew = warp - 8;
     const uint32_t scratch = smem_u32(smem + kTcEpiOff) + (uint32_t)ew * (32 * 33 * 4);
     uint32_t tile_it = 0;
     int Ea_next = row_exp(blockIdx.x, ew * 32 + lane);
@@ -442,33 +443,42 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
       for (int c = 0; c < B.NT; c += 32) {
         const int cc = c + lane;                                    // this lane's column of the slab
         const bool col_ok = cc < B.NT;
-        // C += ...: request the old values of the whole 32 x 32 slab first (32 independent coalesced loads)
-        float old[32];
-        if (a.accumulate) {
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) old[rr] = (col_ok && rr < n_rows) ? cbase[(size_t)rr * a.ldc + cc] : 0.0f;
-        }
         const float fb = col_ok ? __ldg(B.fb + col0 + cc) : 0.0f;
         if (!waited) {
           mbar_wait(&bar_acc_full[buf], (tile_it >> 1) & 1);
           tc_fence_after();
           waited = true;
         }
-        uint32_t v0[32], v1[32];
-        tmem_ld32(lane_base + (uint32_t)c, v0);
-        tmem_ld32(lane_base + (uint32_t)(B.NT + c), v1);
-        tmem_ld_wait();
+        {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(lane_base + (uint32_t)c, v0);
+          tmem_ld32(lane_base + (uint32_t)(B.NT + c), v1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          sts32(scratch + (uint32_t)(lane * 33 + j) * 4, (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * fa);
+          for (int j = 0; j < 32; ++j)
+            sts32(scratch + (uint32_t)(lane * 33 + j) * 4, (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * fa);
+        }
         __syncwarp();
         if (col_ok) {
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            if (rr < n_rows) {
-              float v = lds32(scratch + (uint32_t)(rr * 33 + lane) * 4) * fb;
-              if (a.accumulate) v += old[rr];
-              cbase[(size_t)rr * a.ldc + cc] = v;
+          for (int half = 0; half < 2; ++half) {
+            // C += ...: the 16 old values of this lane's column are requested together (independent coalesced loads)
+            float old[16];
+            if (a.accumulate) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int rr = 16 * half + q;
+                old[q] = rr < n_rows ? cbase[(size_t)rr * a.ldc + cc] : 0.0f;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int rr = 16 * half + q;
+              if (rr < n_rows) {
+                float v = lds32(scratch + (uint32_t)(rr * 33 + lane) * 4) * fb;
+                if (a.accumulate) v += old[q];
+                cbase[(size_t)rr * a.ldc + cc] = v;
+              }
             }
           }
         }
@@ -481,7 +491,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 13) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }

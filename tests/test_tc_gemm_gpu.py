@@ -134,7 +134,9 @@ def _block_linear(n_nodes, a_K, c_N, accumulate, use_tc, seed=0, pad=(32, 64)):
     (1000, [224, 64, 32], [224, 384, 352]),          # ... its transpose (backward)
     (333, [128, 64, 32], [128, 64, 32]),             # self_interaction_1
     (4100, [128, 64, 32], [224, 64, 32]),            # self connection; 33 node tiles: several tiles per CTA
-    (515, [256, 480, 416, 352], [256, 64, 32, 32]),  # lmax 3 shapes
+    (515, [256, 480, 416, 352], [256, 64, 32, 32]),  # lmax 3 shapes (SevenNet-l3i5 self_interaction_2)
+    (515, [256, 64, 32, 32], [256, 480, 416, 352]),  # ... its transpose: column tiles of 128 / 96 / 32 / 32
+    (300, [128, 64, 32, 32], [256, 64, 32, 32]),     # lmax 3 self connection
     (20000, [224, 384, 352], [224, 64, 32]),         # many tiles per CTA: the operand rings wrap many times
 ])
 def test_block_linear_tc_matches_fp64(n_nodes, a_K, c_N, accumulate):

@@ -8,7 +8,8 @@ from sevenn_b200.checkpoint import load_weights
 from sevenn_b200.engine import B200Engine, set_option, STAGE_FWD_BEGIN, STAGE_FWD_LAYER, STAGE_FWD_END, STAGE_BWD_LAYER_A, STAGE_BWD_LAYER_B, STAGE_BWD_END
 from sevenn_b200.neighbors import build_graph, diamond_si
 nc = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-meta, arrays = load_weights(os.path.join(ROOT, 'weights', 'sevennet_0.npz'))
+model = sys.argv[2] if len(sys.argv) > 2 else 'sevennet_0'
+meta, arrays = load_weights(os.path.join(ROOT, 'weights', f'{model}.npz'))
 tm = {int(k): int(v) for k, v in meta['type_map'].items()}
 pos, cell, z = diamond_si(nc, nc, nc)
 ei, ev = build_graph(pos, cell, True, 5.0)

@@ -42,7 +42,7 @@ def run(n_nodes, a_K, c_N, acc, swz, seed=0):
         print(f' block l={l}: bad fraction {bad.mean():.4f}, max err {err.max():.3e}')
         if not bad.any():
             continue
-        NT = N if N <= 128 else N // 2
+        NT = N if N <= 128 else next(N // c for c in range(2, 17) if N % c == 0 and (N // c) % 16 == 0 and N // c <= 128)
         for mt in range((n_nodes + 127) // 128):
             rows = slice(mt * 128, min(n_nodes, mt * 128 + 128))
             for ci in range(d):
@@ -72,7 +72,9 @@ def run(n_nodes, a_K, c_N, acc, swz, seed=0):
                           f'bad rows {rowbad.sum()}/{rowbad.size} bad cols {colbad.sum()}/{colbad.size} first bad row {int(np.argmax(rowbad))}')
 
 
-for cfg in [(777, [224], [112], False, 0), (777, [224], [112], False, 1), (300, [160], [32], False, 0), (300, [192], [32], False, 0),
-            (256, [224], [112], True, 1), (1000, [224], [224], True, 1), (1000, [384], [64], True, 1), (1000, [160], [32], True, 1),
-            (1000, [192], [32], True, 1), (1000, [128, 384], [32, 64], True, 1)]:
+for cfg in [(777, [224], [112], False, 0), (1000, [224, 384, 352], [224, 64, 32], True, 1),
+            (515, [256, 64, 32, 32], [256, 480, 416, 352], False, 1), (515, [256, 64, 32, 32], [256, 480, 416, 352], True, 1),
+            (515, [128, 64, 32, 32], [256, 64, 32, 32], False, 1), (515, [256, 64, 32, 32], [128, 64, 32, 32], False, 1),
+            (515, [128, 64, 32, 32], [128, 64, 32, 32], True, 1), (515, [256, 480, 416, 352], [256, 64, 32, 32], True, 1),
+            (3, [256, 64, 32, 32], [256, 480, 416, 352], False, 1), (64, [256, 64, 32, 32], [256, 480, 416, 352], False, 1)]:
     run(*cfg)
