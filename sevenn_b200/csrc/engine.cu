@@ -354,13 +354,15 @@ struct TcWeights {
   struct Blk { int K, N, NT; size_t q_off, fb_off; } blk[kMaxL];
 };
 
+// column tiling of an N-wide block: as few tiles of <= 128 columns as possible, tile width a multiple of 16;
+// the last tile may be padded (zero weights, masked in the epilogue)
 static int tc_pick_nt(int N) {
-  if (N % 16 != 0) return 0;
-  if (N <= kTcMaxNT) return N;
-  for (int c = 2; c <= 16; ++c)
-    if (N % c == 0 && (N / c) % 16 == 0 && N / c <= kTcMaxNT) return N / c;
-  return 0;
+  if (N <= 0) return 0;
+  const int tiles = (N + kTcMaxNT - 1) / kTcMaxNT;
+  const int w = (N + tiles - 1) / tiles;
+  return (w + 15) / 16 * 16;
 }
+static int tc_tiles(int N, int NT) { return (N + NT - 1) / NT; }
 
 static inline uint16_t bf16_bits_exact(float v) {   // v has <= 8 significant bits: truncation is exact
   uint32_t u;
@@ -370,7 +372,7 @@ static inline uint16_t bf16_bits_exact(float v) {   // v has <= 8 significant bi
 
 // W [K, N] row-major (fp32) -> q [(N/NT) * (K/32) * 3 * NT*32] bf16 bits, fb [N].  Host only.
 static void tc_pack_block(const float* W, int K, int N, int NT, uint16_t* q, float* fb) {
-  const int n_kc = K / kTcKC, n_nt = N / NT;
+  const int n_kc = K / kTcKC;
   for (int n = 0; n < N; ++n) {
     double amax = 0.0;
     for (int k = 0; k < K; ++k) amax = std::max(amax, (double)fabsf(W[(size_t)k * N + n]));
@@ -396,7 +398,6 @@ static void tc_pack_block(const float* W, int K, int N, int NT, uint16_t* q, flo
         q[(((size_t)nt * n_kc + kc) * 3 + sidx) * ((size_t)NT * kTcKC) + elem] = bf16_bits_exact((float)sl[sidx]);
     }
   }
-  (void)n_nt;
 }
 
 static int tc_build_weights(TcWeights& w, const float* host, const int* Ks, const int* Ns, int n_l) {
@@ -410,7 +411,7 @@ static int tc_build_weights(TcWeights& w, const float* host, const int* Ks, cons
     if (NT == 0 || K % kTcKC != 0) return 0;          // not expressible: caller keeps the SIMT kernel
     TcWeights::Blk& b = w.blk[w.nblocks++];
     b = {K, N, NT, q_total, fb_total};
-    q_total += (size_t)3 * K * N;
+    q_total += (size_t)3 * K * NT * tc_tiles(N, NT);
     fb_total += (size_t)N;
   }
   std::vector<uint16_t> q(q_total);
@@ -468,10 +469,9 @@ static int launch_row_exponents(RowExp& re, const float* A, int lda, const int* 
   if (rows == 0 || n_nodes == 0) return 0;
   if (re.buf.ensure((size_t)n_nodes * rows * sizeof(int))) return fail("cudaMalloc failed for row exponents");
   r.E = re.buf.as<int>();
-  const long long total = (long long)n_nodes * rows;
+  if (rows > 16) return fail("row exponents: more than 16 rows per node");
   const int blk = 256, wpb = blk / 32;
-  const int grd = (int)std::min<long long>((total + wpb - 1) / wpb, 148LL * 16);
-  row_exponent_kernel<<<grd, blk, 0, st>>>(r);
+  row_exponent_kernel<<<(n_nodes + wpb - 1) / wpb, blk, 0, st>>>(r);
   S7B_LAUNCH_CHECK();
   return 0;
 }
@@ -506,11 +506,12 @@ static int launch_tc_linear(const TcWeights& w, const RowExp& re, const float* A
     b.K = a_K[l];
     b.N = c_N[l];
     b.NT = w.blk[bi].NT;
+    b.nnt = tc_tiles(b.N, b.NT);
     b.c_off = c_off[l];
     b.c_cs = c_N[l];
     b.row_base = rows;
     b.tile0 = tiles;
-    tiles += n_mt * b.d * (b.N / b.NT);
+    tiles += n_mt * b.d * b.nnt;
     rows += 2 * l + 1;
     // A block viewed as (k, component, node): strides K*4 and lda*4 bytes
     const cuuint64_t gdim[3] = {(cuuint64_t)b.K, (cuuint64_t)b.d, (cuuint64_t)n_nodes};
@@ -682,7 +683,7 @@ int s7b_dense_linear(const float* A, const float* W, float* C, int64_t rows, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (rows <= 0 || K <= 0 || N <= 0 || rows > (1 << 24)) return fail("bad sizes");
   if (!use_tc) return dense_gemm(A, K, C, N, W, rows, kEpiNone, nullptr, nullptr, false, st);
-  if (K % kTcKC != 0 || tc_pick_nt(N) == 0) return fail("tensor-core linear needs K % 32 == 0 and N a multiple of 16 that splits into tiles <= 128");
+  if (K % kTcKC != 0) return fail("tensor-core linear needs K % 32 == 0");
   std::vector<float> hw((size_t)K * N);
   S7B_CUDA_CHECK(cudaMemcpyAsync(hw.data(), W, hw.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
   S7B_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -736,11 +737,13 @@ int s7b_block_linear(const float* A, int32_t lda, int32_t n_nodes, int32_t n_l, 
 }
 
 // Host-only: the tensor-core weight packing of tc_gemm.cuh for one [K, N] block (tests/test_tc_pack_cpu.py).
-// q: 3*K*N uint16 (bf16 bits), laid out [n tile][K/32][slice][canonical NT x 32]; fb: N floats; *NT_out = tile width.
+// q: 3*K*NT*ceil(N/NT) uint16 (bf16 bits; caller allocates 3*K*(N+127) and zero-fills), laid out
+// [n tile][K/32][slice][canonical NT x 32]; fb: N floats; *NT_out = tile width.
 int s7b_tc_pack_weights(const float* W, int32_t K, int32_t N, uint16_t* q, float* fb, int32_t* NT_out) {
   if (!W || !q || !fb) return fail("null argument");
   const int NT = tc_pick_nt(N);
   if (K <= 0 || K % kTcKC != 0 || NT == 0) return fail("unsupported shape for the tensor-core linear");
+  memset(q, 0, (size_t)3 * K * NT * tc_tiles(N, NT) * sizeof(uint16_t));
   tc_pack_block(W, K, N, NT, q, fb);
   if (NT_out) *NT_out = NT;
   return 0;
@@ -1337,6 +1340,7 @@ void* s7b_engine_buffer(S7bEngine* e, const char* name, int layer, size_t* numel
   else if (nm == "gate_in" && in_range(layer)) { p = e->g[layer].p; n = (size_t)e->n_local * e->layers[layer].dim_g; }
   else if (nm == "weight" && in_range(layer)) { p = e->wbuf[layer].p; n = (size_t)e->n_edges * e->layers[layer].W; }
   else if (nm == "dx" && in_range(layer)) { p = e->dx.p; n = (size_t)e->n_nodes * e->layers[layer].dim_x; }
+  else if (nm == "dg" && in_range(layer)) { p = e->dg.p; n = (size_t)e->n_local * e->layers[layer].dim_g; }
   else if (nm == "mid" && in_range(layer)) { p = e->mid.p; n = (size_t)e->n_local * e->layers[layer].dim_mid; }
   else if (nm == "h" && in_range(layer)) { p = e->h.p; n = (size_t)e->n_local * e->layers[layer].dim_h; }
   else if (nm == "dh" && in_range(layer)) { p = e->dh.p; n = (size_t)e->n_local * e->layers[layer].dim_x; }

@@ -168,39 +168,39 @@ struct RowExpArgs {
 };
 
 __global__ void row_exponent_kernel(const RowExpArgs a) {
-  const int warps_per_block = blockDim.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const long long total = (long long)a.n_nodes * a.rows_per_node;
-  for (long long w = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < total;
-       w += (long long)gridDim.x * warps_per_block) {
-    const int n = (int)(w / a.rows_per_node);
-    const int rr = (int)(w - (long long)n * a.rows_per_node);
-    int b = 0;
-    while (b + 1 < a.nblocks && rr >= a.row_base[b + 1]) ++b;
-    const int i = rr - a.row_base[b];
-    const float4* row = reinterpret_cast<const float4*>(a.A + (size_t)n * a.lda + a.a_off[b] + (size_t)i * a.K[b]);
-    uint32_t m = 0;
-    for (int q = lane; q < (a.K[b] >> 2); q += 32) {
-      const float4 v = __ldg(row + q);
-      m = max(m, __float_as_uint(v.x) & 0x7fffffffu);
-      m = max(m, __float_as_uint(v.y) & 0x7fffffffu);
-      m = max(m, __float_as_uint(v.z) & 0x7fffffffu);
-      m = max(m, __float_as_uint(v.w) & 0x7fffffffu);
+  // one warp per node: the node's row is read once, coalesced (float4 per lane); every float4 lies inside one
+  // (block, component) row (K is a multiple of 4), whose running maximum is kept in shared memory
+  __shared__ unsigned int smax[8][16];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (lane < 16) smax[wib][lane] = 0u;
+  __syncwarp();
+  if (n < a.n_nodes) {
+    for (int b = 0; b < a.nblocks; ++b) {
+      const int K = a.K[b], quads = (a.d[b] * K) >> 2;
+      const float4* row = reinterpret_cast<const float4*>(a.A + (size_t)n * a.lda + a.a_off[b]);
+      for (int q = lane; q < quads; q += 32) {
+        const float4 v = __ldg(row + q);
+        unsigned int m = __float_as_uint(v.x) & 0x7fffffffu;
+        m = max(m, __float_as_uint(v.y) & 0x7fffffffu);
+        m = max(m, __float_as_uint(v.z) & 0x7fffffffu);
+        m = max(m, __float_as_uint(v.w) & 0x7fffffffu);
+        atomicMax(&smax[wib][a.row_base[b] + (4 * q) / K], m);
+      }
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
-    if (lane == 0) {
-      const int ex = (int)(m >> 23);
-      a.E[w] = (ex == 0 || ex == 255) ? kTcZeroRow : ex - 126;     // |a| < 2^(ex-126)
-    }
+  }
+  __syncwarp();
+  if (n < a.n_nodes && lane < a.rows_per_node) {
+    const int ex = (int)(smax[wib][lane] >> 23);
+    a.E[(size_t)n * a.rows_per_node + lane] = (ex < 30 || ex == 255) ? kTcZeroRow : ex - 126;     // |a| < 2^(ex-126)
   }
 }
 
 // ---- the GEMM --------------------------------------------------------------------------------------
 struct TcLinBlock {
-  const uint16_t* Wq;   // pre-sliced weights: [n_ntiles][K/32][3 slices][canonical NT x 32 bf16]
+  const uint16_t* Wq;   // pre-sliced weights: [nnt][K/32][3 slices][canonical NT x 32 bf16]
   const float* fb;      // [N] column scales 2^(Eb-7)
-  int d, K, N, NT;
+  int d, K, N, NT, nnt;  // nnt column tiles of NT columns each (nnt * NT >= N; the pad columns carry zero weights)
   int c_off, c_cs;
   int row_base;         // first row of this block in the row-exponent array
   int tile0;            // index of the block's first tile; tiles ordered [node tile][component][n tile]
@@ -270,7 +270,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
     b = 0;
     while (b + 1 < a.nblocks && t >= a.blk[b + 1].tile0) ++b;
     const int rel = t - a.blk[b].tile0;
-    const int nnt = a.blk[b].N / a.blk[b].NT;
+    const int nnt = a.blk[b].nnt;
     nt = rel % nnt;
     const int r2 = rel / nnt;
     ci = r2 % a.blk[b].d;
@@ -442,7 +442,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
       bool waited = false;
       for (int c = 0; c < B.NT; c += 32) {
         const int cc = c + lane;                                    // this lane's column of the slab
-        const bool col_ok = cc < B.NT;
+        const bool col_ok = cc < B.NT && col0 + cc < B.N;          // the last column tile may be padded
         const float fb = col_ok ? __ldg(B.fb + col0 + cc) : 0.0f;
         if (!waited) {
           mbar_wait(&bar_acc_full[buf], (tile_it >> 1) & 1);
@@ -460,25 +460,15 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         }
         __syncwarp();
         if (col_ok) {
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            // C += ...: the 16 old values of this lane's column are requested together (independent coalesced loads)
-            float old[16];
-            if (a.accumulate) {
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int rr = 16 * half + q;
-                old[q] = rr < n_rows ? cbase[(size_t)rr * a.ldc + cc] : 0.0f;
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const int rr = 16 * half + q;
-              if (rr < n_rows) {
-                float v = lds32(scratch + (uint32_t)(rr * 33 + lane) * 4) * fb;
-                if (a.accumulate) v += old[q];
-                cbase[(size_t)rr * a.ldc + cc] = v;
-              }
+          // C = v, or C += v as a fire-and-forget reduction (RED.ADD.F32): every element of C belongs to exactly
+          // one tile, so the single add per element is deterministic and no load latency enters the epilogue
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < n_rows) {
+              const float v = lds32(scratch + (uint32_t)(rr * 33 + lane) * 4) * fb;
+              float* p = cbase + (size_t)rr * a.ldc + cc;
+              if (a.accumulate) atomicAdd(p, v);
+              else *p = v;
             }
           }
         }

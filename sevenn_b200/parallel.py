@@ -94,6 +94,70 @@ def brick_decompose(pos: np.ndarray, cell: np.ndarray, species: np.ndarray, grid
                 n_global=int(len(pos)))
 
 
+def device_brick_partition(engine, pos: np.ndarray, cell: np.ndarray, species: np.ndarray, grid: Sequence[int],
+                           rank: int, pbc=True) -> Dict[str, object]:
+    """The same local view as ``brick_decompose`` built per step ON THE DEVICE from positions (the
+    reference's per-step ghost / edge build, ``pair_e3gnn_parallel.cpp:194-340, 698-799``): the engine's cell-list
+    kernels produce the neighbour rows of this rank's atoms against all atoms
+    (``s7b_engine_neighbor_rows_host``); ghost rows, interior/boundary order, the local edge list and the send
+    lists are then derived with device-side sorts / scans (torch) -- no global neighbour list, no host loop over
+    edges.  Because "j is a ghost of rank q" is the same statement as "j has a neighbour owned by q", every
+    rank derives its SEND lists from its own rows: peers need no handshake (``GhostExchange.from_lists``).
+
+    Every rank passes the same global ``pos`` / ``species`` (replicated, 24 B per atom).  Returns the ``part``
+    dict of ``brick_decompose`` with device tensors for the graph arrays plus ``send_lists``."""
+    import torch
+    dev = engine.device
+    pos = np.asarray(pos, dtype=np.float64)
+    cell = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    n_global = len(pos)
+    frac = pos @ np.linalg.inv(cell)
+    frac -= np.floor(frac)
+    owner = owner_of(frac, grid)                                     # O(N) on the host: 8 B per atom
+    mine = np.nonzero(owner == rank)[0]
+    n_mine = len(mine)
+    rowptr, src_g, vec = engine.neighbor_rows(species, pos, cell, pbc, mine)
+    rowptr, src_g, vec = rowptr.long(), src_g.long(), vec.clone()
+    owner_t = torch.as_tensor(owner, device=dev)
+    mine_t = torch.as_tensor(mine, device=dev)
+    counts = rowptr[1:] - rowptr[:-1]
+    centre = torch.repeat_interleave(torch.arange(n_mine, device=dev), counts)      # owned-row index of every edge
+    src_owner = owner_t[src_g]
+    remote = src_owner != rank
+    # interior (no remote neighbour) first, boundary last; global order inside each class
+    is_b = torch.zeros(n_mine, dtype=torch.bool, device=dev)
+    is_b[centre[remote]] = True
+    order = torch.cat([torch.nonzero(~is_b).flatten(), torch.nonzero(is_b).flatten()])
+    n_interior = int((~is_b).sum())
+    new_of_old = torch.empty(n_mine, dtype=torch.long, device=dev)
+    new_of_old[order] = torch.arange(n_mine, device=dev)
+    # ghosts: unique remote neighbours ordered by (owner, global id)
+    gkey = torch.unique(src_owner[remote] * n_global + src_g[remote])
+    ghost_owner, ghost_gid = gkey // n_global, gkey % n_global
+    n_ghost = int(gkey.numel())
+    lookup = torch.full((n_global,), -1, dtype=torch.long, device=dev)
+    lookup[mine_t[order]] = torch.arange(n_mine, device=dev)
+    lookup[ghost_gid] = n_mine + torch.arange(n_ghost, device=dev)
+    # local edge list, rows in the new order (stable: neighbour order inside a row is kept)
+    new_centre = new_of_old[centre]
+    perm = torch.argsort(new_centre, stable=True)
+    src_l = lookup[src_g][perm]
+    vec_l = vec[perm].contiguous()
+    rowptr_l = torch.zeros(n_mine + 1, dtype=torch.long, device=dev)
+    rowptr_l[1:] = torch.cumsum(torch.bincount(new_centre, minlength=n_mine), 0)
+    # send lists: my atoms that have a neighbour owned by q, ordered by global id (= q's ghost-row order)
+    skey = torch.unique(src_owner[remote] * n_global + mine_t[centre[remote]])
+    s_owner, s_gid = skey // n_global, skey % n_global
+    world = int(np.prod(grid))
+    send_lists = [lookup[s_gid[s_owner == q]] for q in range(world)]
+    gids = torch.cat([mine_t[order], ghost_gid])
+    species_t = torch.as_tensor(np.asarray(species), device=dev)[gids].to(torch.int32)
+    return dict(global_ids=gids.cpu().numpy(), species=species_t, n_local=n_mine, n_nodes=n_mine + n_ghost,
+                n_interior=n_interior, rowptr=rowptr_l.to(torch.int32), src=src_l.to(torch.int32), edge_vec=vec_l,
+                ghost_owner=ghost_owner.cpu().numpy(), n_global=n_global, send_lists=send_lists,
+                recv_counts=[int((ghost_owner == q).sum()) for q in range(world)])
+
+
 class GhostExchange:
     """Index maps + the two collectives (forward fill, reverse sum) over torch.distributed."""
 
@@ -147,6 +211,28 @@ class GhostExchange:
         self.send_idx32 = [i.to(torch.int32).contiguous() for i in self.send_idx]
         self.send_idx_all32 = self.send_idx_all.to(torch.int32).contiguous()
         self._bufs = {}
+
+    @classmethod
+    def from_lists(cls, part, device, group=None, engine=None):
+        """Index maps from a ``device_brick_partition`` result: receive counts per owner and the locally
+        derived send lists -- no handshake between the ranks."""
+        import torch
+        import torch.distributed as dist
+        self = cls.__new__(cls)
+        self.torch, self.dist, self.group, self.device = torch, dist, group, device
+        self.kernels = engine if (engine is not None and hasattr(engine, 'gather_rows')) else None
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n_local, self.n_nodes = part['n_local'], part['n_nodes']
+        self.recv_counts = list(part['recv_counts'])
+        self.recv_off = np.concatenate([[0], np.cumsum(self.recv_counts)]).astype(np.int64)
+        self.send_idx = [t.to(device).long() for t in part['send_lists']]
+        self.send_counts = [int(t.numel()) for t in self.send_idx]
+        self.n_ghost = int(sum(self.recv_counts))
+        self.send_idx_all = torch.cat(self.send_idx) if self.send_idx else torch.zeros(0, dtype=torch.long, device=device)
+        self.send_idx32 = [i.to(torch.int32).contiguous() for i in self.send_idx]
+        self.send_idx_all32 = self.send_idx_all.to(torch.int32).contiguous()
+        self._bufs = {}
+        return self
 
     def _packed(self, width, dtype, device):
         """persistent [sum(send_counts), width] staging buffer: no allocator traffic on the step path"""
@@ -219,8 +305,12 @@ class DistributedRunner:
         self.n_layers = engine.spec.n_layers
         self.n_local, self.n_nodes = part['n_local'], part['n_nodes']
         self.n_interior = int(part.get('n_interior', self.n_local))
-        self.exchange = GhostExchange(part, self.device, group, engine)
-        engine.set_graph(part['species'], part['edge_index'], part['edge_vec'], n_local=self.n_local)
+        if 'send_lists' in part:            # device_brick_partition: CSR on the device, send lists derived locally
+            self.exchange = GhostExchange.from_lists(part, self.device, group, engine)
+            engine.set_graph_csr(part['species'], part['rowptr'], part['src'], part['edge_vec'], self.n_local)
+        else:
+            self.exchange = GhostExchange(part, self.device, group, engine)
+            engine.set_graph(part['species'], part['edge_index'], part['edge_vec'], n_local=self.n_local)
         self.split = hasattr(engine, 'set_interior')
         if self.split:
             engine.set_interior(self.n_interior)
@@ -232,6 +322,30 @@ class DistributedRunner:
 
     def _buf(self, name, t, width):
         return self.engine.buffer(name, t, shape=(self.n_nodes, width))
+
+    @classmethod
+    def from_positions(cls, engine, pos, cell, species, grid, group=None, cuda_graph: Optional[bool] = False):
+        """positions in: partition, ghost lists and the graph are built on the device (``device_brick_partition``)"""
+        import torch.distributed as dist
+        part = device_brick_partition(engine, pos, cell, species, grid, dist.get_rank(group))
+        run = cls(engine, part, group, cuda_graph=cuda_graph)
+        run._grid, run._species, run._cell = tuple(grid), np.asarray(species), np.asarray(cell, dtype=np.float64)
+        return run
+
+    def update_positions(self, pos, cell=None):
+        """MD step: re-partition from the new positions on the device (atoms may change owner; ghost and edge
+        counts change, so this path runs the eager stage sequence -- a captured CUDA graph bakes the sizes in)."""
+        if cell is not None:
+            self._cell = np.asarray(cell, dtype=np.float64)
+        part = device_brick_partition(self.engine, pos, self._cell, self._species, self._grid, self.dist.get_rank(self.group))
+        self.part = part
+        self.n_local, self.n_nodes, self.n_interior = part['n_local'], part['n_nodes'], part['n_interior']
+        self.exchange = GhostExchange.from_lists(part, self.device, self.group, self.engine)
+        self.engine.set_graph_csr(part['species'], part['rowptr'], part['src'], part['edge_vec'], self.n_local)
+        if self.split:
+            self.engine.set_interior(self.n_interior)
+        self._graph, self._host = None, None
+        return self
 
     def _all_reduce_f8(self, name):
         buf = self.engine.buffer(name, dtype='f8')

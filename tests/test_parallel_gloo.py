@@ -213,3 +213,60 @@ def test_brick_decompose_invariants():
         mask = np.isin(ei[0], gids[:nl])
         ref = {(int(a), int(b), tuple(np.round(v, 6))) for a, b, v in zip(ei[0][mask], ei[1][mask], ev[mask])}
         assert g_edges == ref
+
+
+class _RowsEngine:
+    """CPU stand-in for B200Engine.neighbor_rows (the device cell-list kernels): numpy neighbour list
+    restricted to the requested centre atoms."""
+    device = torch.device('cpu')
+
+    def neighbor_rows(self, species, positions, cell, pbc, centres):
+        ei, ev = build_graph(np.asarray(positions), np.asarray(cell), True, 5.0)
+        centres = np.asarray(centres)
+        pos_of = -np.ones(len(positions), dtype=np.int64)
+        pos_of[centres] = np.arange(len(centres))
+        keep = pos_of[ei[0]] >= 0
+        c, s, v = pos_of[ei[0][keep]], ei[1][keep], ev[keep]
+        o = np.argsort(c, kind='stable')
+        rowptr = np.zeros(len(centres) + 1, dtype=np.int64)
+        np.cumsum(np.bincount(c, minlength=len(centres)), out=rowptr[1:])
+        return (torch.as_tensor(rowptr, dtype=torch.int32), torch.as_tensor(s[o], dtype=torch.int32),
+                torch.as_tensor(v[o], dtype=torch.float32))
+
+
+@pytest.mark.parametrize('grid,kind', [((2, 1, 1), 'si_long'), ((2, 2, 1), 'si'), ((1, 1, 2), 'nacl')])
+def test_device_partition_equals_host_partition(grid, kind):
+    """device_brick_partition (per-step, from positions, send lists derived locally) describes the same local
+    systems as brick_decompose (global numpy neighbour list) -- same atoms in the same rows, same edges, and
+    send lists that match what the peers expect in their ghost rows."""
+    from sevenn_b200.parallel import device_brick_partition
+    pos, cell, species = _system(kind)
+    world = int(np.prod(grid))
+    host = [brick_decompose(pos, cell, species, grid, r, 5.0) for r in range(world)]
+    devp = [device_brick_partition(_RowsEngine(), pos, cell, species, grid, r) for r in range(world)]
+    for r in range(world):
+        h, d = host[r], devp[r]
+        assert (h['n_local'], h['n_nodes'], h['n_interior']) == (d['n_local'], d['n_nodes'], d['n_interior'])
+        assert np.array_equal(h['global_ids'], d['global_ids'])
+        assert np.array_equal(h['species'], d['species'].numpy())
+        assert np.array_equal(h['ghost_owner'], d['ghost_owner'])
+        rp, src, vec = d['rowptr'].numpy(), d['src'].numpy(), d['edge_vec'].numpy()
+        assert rp[-1] == h['edge_index'].shape[1]
+        cen = np.repeat(np.arange(d['n_local']), np.diff(rp))
+
+        def canon(c, s, v):
+            o = np.lexsort((np.round(v[:, 2], 3), np.round(v[:, 1], 3), np.round(v[:, 0], 3), s, c))
+            return c[o], s[o], v[o]
+        hc, hs, hv = canon(h['edge_index'][0], h['edge_index'][1], np.asarray(h['edge_vec'], dtype=np.float64))
+        dc, ds, dv = canon(cen, src, vec.astype(np.float64))
+        assert np.array_equal(hc, dc) and np.array_equal(hs, ds) and np.allclose(hv, dv, atol=1e-5)
+        # what rank r sends to q is exactly what q holds as ghosts owned by r, in q's ghost-row order
+        for q in range(world):
+            if q == r:
+                assert d['send_lists'][q].numel() == 0
+                continue
+            sent_gids = d['global_ids'][d['send_lists'][q].numpy()]
+            dq = devp[q]
+            ghosts_q = dq['global_ids'][dq['n_local']:][dq['ghost_owner'] == r]
+            assert np.array_equal(sent_gids, ghosts_q)
+            assert dq['recv_counts'][r] == len(sent_gids)

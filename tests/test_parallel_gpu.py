@@ -48,8 +48,22 @@ def _worker(rank, world, port, grid, model, q):
         assert abs(float(r['energy'].cpu()[0]) - float(r_eager['energy'].cpu()[0])) < 1e-9
         assert torch.allclose(r['forces'], r_eager['forces'], atol=2e-6)
         h = run.compute_host()
+        # positions in: partition, ghost lists and graph built on the device, send lists derived locally
+        rp = DistributedRunner.from_positions(B200Engine(meta, arrays, device=rank), pos, cell, species_of(meta, z), grid)
+        rp.compute()
+        torch.cuda.synchronize()
+        r2 = rp.results()
+        assert abs(float(r2['energy'].cpu()[0]) - float(r['energy'].cpu()[0])) < 2e-5
+        assert np.array_equal(r2['global_ids'], r['global_ids'])
+        assert torch.allclose(r2['forces'], r['forces'], atol=5e-6)
+        moved = pos + np.random.RandomState(9).normal(scale=0.03, size=pos.shape)
+        rp.update_positions(moved)
+        rp.compute()
+        torch.cuda.synchronize()
+        r3 = rp.results()
         q.put((rank, r['global_ids'], r['forces'].cpu().numpy(), float(r['energy'].cpu()[0]),
-               r['atomic_energy'].cpu().numpy(), r['virial'].cpu().numpy(), h['energy'], h['forces'].copy()))
+               r['atomic_energy'].cpu().numpy(), r['virial'].cpu().numpy(), h['energy'], h['forces'].copy(),
+               r3['global_ids'], r3['forces'].cpu().numpy(), float(r3['energy'].cpu()[0])))
     finally:
         dist.destroy_process_group()
 
@@ -78,9 +92,15 @@ def test_multi_gpu_matches_oracle(world, grid, model):
         assert p.exitcode == 0
     forces = np.zeros((len(pos), 3))
     forces_h = np.zeros((len(pos), 3))
+    forces_m = np.zeros((len(pos), 3))
     ae = np.zeros(len(pos))
-    for rank, gids, f, energy, a, virial, e_h, f_h in res:
+    moved = pos + np.random.RandomState(9).normal(scale=0.03, size=pos.shape)
+    ei_m, ev_m = build_graph(moved, cell, True, 5.0)
+    ref_m = oracle(model).forward(species_of(meta, z), ei_m, ev_m)
+    for rank, gids, f, energy, a, virial, e_h, f_h, gids_m, f_m, e_m in res:
         forces[gids], forces_h[gids], ae[gids] = f, f_h, a
+        forces_m[gids_m] = f_m
+        assert abs(e_m - float(ref_m['energy'])) < 1e-4      # after update_positions: re-partitioned on the device
         assert abs(energy - float(ref['energy'])) < 1e-4
         assert abs(e_h - energy) < 1e-6
         # virial = sum over ~4000 edges of r (x) f in fp32 products: fp32 edge-force noise (~5e-6 eV/A)
@@ -88,6 +108,7 @@ def test_multi_gpu_matches_oracle(world, grid, model):
         assert np.allclose(virial, ref['virial'].numpy(), atol=5e-3, rtol=1e-5)
     assert np.allclose(forces, ref['forces'].numpy(), atol=5e-5)
     assert np.allclose(forces_h, forces, atol=5e-6)
+    assert np.allclose(forces_m, ref_m['forces'].numpy(), atol=5e-5)
     assert np.allclose(ae, ref['atomic_energy'].numpy(), atol=2e-5)
 
 

@@ -15,7 +15,7 @@ def _pack(W):
     lib = load_library()
     K, N = W.shape
     W = np.ascontiguousarray(W, dtype=np.float32)
-    q = np.zeros(3 * K * N, dtype=np.uint16)
+    q = np.zeros(3 * K * (N + 127), dtype=np.uint16)
     fb = np.zeros(N, dtype=np.float32)
     nt = ctypes.c_int32()
     check(lib.s7b_tc_pack_weights(W.ctypes.data, K, N, q.ctypes.data, fb.ctypes.data, ctypes.byref(nt)))
@@ -27,11 +27,15 @@ def _pack(W):
     r = np.arange(NT)[:, None]
     kk = np.arange(32)[None, :]
     elem = ((r & 7) * 16 + (r >> 3) * 512 + (kk >> 3) * 128 + (kk & 7) * 2) // 2
-    for t in range(N // NT):
+    tiles = (N + NT - 1) // NT
+    padded = np.zeros((3, tiles * NT, K))
+    for t in range(tiles):
         for kc in range(n_kc):
             for s in range(3):
                 base = ((t * n_kc + kc) * 3 + s) * NT * 32
-                out[s, t * NT:(t + 1) * NT, kc * 32:(kc + 1) * 32] = vals[base + elem]
+                padded[s, t * NT:(t + 1) * NT, kc * 32:(kc + 1) * 32] = vals[base + elem]
+    assert not padded[:, N:].any()                      # pad columns of the last tile carry zero weights
+    out[:] = padded[:, :N]
     return out, fb.astype(np.float64), NT
 
 
@@ -56,13 +60,13 @@ def _slice_rows(A):
     return q0.astype(np.float64), q1.astype(np.float64) / 256.0, q2.astype(np.float64) / 65536.0, fa
 
 
-@pytest.mark.parametrize('K,N', [(32, 32), (224, 224), (384, 64), (352, 32), (64, 384), (256, 256), (32, 352)])
+@pytest.mark.parametrize('K,N', [(32, 32), (224, 224), (384, 64), (352, 32), (64, 384), (256, 256), (32, 352), (64, 480), (32, 416), (32, 24)])
 def test_pack_reproduces_weights(K, N):
     rng = np.random.RandomState(K + N)
     W = (rng.normal(size=(K, N)) / np.sqrt(K)).astype(np.float32)
     W[:, 0] = 0.0                                      # an all-zero column
     sl, fb, NT = _pack(W)
-    assert NT <= 128 and N % NT == 0 and NT % 16 == 0
+    assert NT <= 128 and NT % 16 == 0 and (N + NT - 1) // NT == (N + 127) // 128     # fewest tiles of <= 128 columns
     rec = (sl.sum(0) * fb[:, None]).T                  # [K, N]
     bound = np.abs(W).max(axis=0)
     assert np.all(np.abs(rec - W) <= np.maximum(bound, 1e-30) * 2.0 ** -23 + 1e-30)
