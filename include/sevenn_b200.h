@@ -124,6 +124,11 @@ S7B_API int s7b_block_linear(const float* A, int32_t lda, int32_t n_nodes, int32
                              const int32_t* a_K, const float* W_host, float* C, int32_t ldc, const int32_t* c_off,
                              const int32_t* c_N, int32_t accumulate, int32_t use_tc, void* stream);
 
+/* Debug aid: timeline (role, event, index, clock64) of CTA 0 of the following tensor-core linear launches,
+ * written to a device buffer of 8 + 3 * cap int64 (words 1..5 = records of each of the five roles, then cap / 5
+ * records {event, index, clock64} per role); cap = 0 switches it off. */
+S7B_API int s7b_tc_trace_enable(int32_t cap, void** device_buffer);
+
 /* Host-only helper (no GPU needed): the weight packing of the tensor-core linear for one [K, N] block --
  * three signed 8-bit fixed-point slices per weight as bf16, in the shared-memory layout the kernel
  * consumes (sevenn_b200/csrc/tc_gemm.cuh).  q: 3*K*N uint16, fb: N column scales, *NT: tile width. */

@@ -312,6 +312,8 @@ static int g_opt_atomic_virial = 0;   // engines created afterwards also produce
 static int g_opt_concurrent = 1;   // co-schedule the per-l1 convolution kernels of a layer on side streams
 static int g_opt_cuda_graph = 1;   // s7b_engine_compute replays a captured CUDA graph of the step (table mode)
 static int g_opt_tc_gemm = 1;   // 1 (default): node linears on tcgen05 (error-free bf16x3 slices, tc_gemm.cuh); 0: FP32 SIMT
+static long long* g_tc_trace = nullptr;   // device buffer [1 + 4 * cap] when s7b_tc_trace_enable was called (debug)
+static int g_tc_trace_cap = 0;
 static int g_opt_tc_swizzle = 1;   // 128B-swizzled TMA tile for the raw A chunk (0: plain rows; A/B switch)
 
 __global__ void set_i64_kernel(int64_t* p, int64_t v) { *p = v; }
@@ -483,6 +485,9 @@ static int launch_tc_linear(const TcWeights& w, const RowExp& re, const float* A
                             int n_nodes, bool accumulate, cudaStream_t st) {
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return fail("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  if (ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(C) & 15) != 0) return fail("tensor-core linear: C rows must be 16-byte aligned");
+  for (int l = 0; l < n_l; ++l)
+    if (c_N[l] != 0 && a_K[l] != 0 && (c_N[l] % 4 != 0 || c_off[l] % 4 != 0)) return fail("tensor-core linear: output blocks must be multiples of 4 floats");
   TcLinArgs t;
   TcMaps maps;
   memset(&t, 0, sizeof(t));
@@ -494,6 +499,8 @@ static int launch_tc_linear(const TcWeights& w, const RowExp& re, const float* A
   t.rows_per_node = re.rows_per_node;
   t.accumulate = accumulate ? 1 : 0;
   t.swizzle = g_opt_tc_swizzle;
+  t.trace = g_tc_trace;
+  t.trace_cap = g_tc_trace_cap;
   const int n_mt = (n_nodes + kTcBM - 1) / kTcBM;
   int tiles = 0, rows = 0, bi = 0;
   for (int l = 0; l < n_l; ++l) {
@@ -699,6 +706,20 @@ int s7b_dense_linear(const float* A, const float* W, float* C, int64_t rows, int
   w.fb.release();
   re.buf.release();
   return rc;
+}
+
+// Debug: record a timeline of CTA 0 of the NEXT tensor-core linear launches into a device buffer the caller
+// reads back (tools/tc_trace.py).  cap = 0 turns tracing off.  Returns the device pointer through *buf.
+int s7b_tc_trace_enable(int32_t cap, void** buf) {
+  if (g_tc_trace) { cudaFree(g_tc_trace); g_tc_trace = nullptr; }
+  g_tc_trace_cap = 0;
+  if (cap > 0) {
+    S7B_CUDA_CHECK(cudaMalloc((void**)&g_tc_trace, (8 + 3 * (size_t)cap) * sizeof(long long)));
+    S7B_CUDA_CHECK(cudaMemset(g_tc_trace, 0, (8 + 3 * (size_t)cap) * sizeof(long long)));
+    g_tc_trace_cap = cap;
+  }
+  if (buf) *buf = g_tc_trace;
+  return 0;
 }
 
 // Test / utility entry: one block-diagonal irreps linear  C_l (+)= A_l W_l  (l = 0..n_l-1, block l has 2l+1

@@ -54,7 +54,7 @@ constexpr int kTcRawOff = 0;
 constexpr int kTcOpsOff = kTcRawOff + kTcRawStages * kTcRawBytes;
 constexpr int kTcWOff = kTcOpsOff + kTcOpsStages * kTcOpsBytes;
 constexpr int kTcEpiOff = kTcWOff + kTcWStages * kTcWBytes;
-constexpr int kTcEpiBytes = 4 * 32 * 33 * 4;              // per-warp 32 x 33 transpose scratch
+constexpr int kTcEpiBytes = 4 * 32 * 36 * 4;              // per-warp 32 x 36 transpose scratch (16-byte aligned rows)
 constexpr int kTcSmemBytes = kTcEpiOff + kTcEpiBytes + 1024 /*alignment slack*/;
 constexpr int kTcZeroRow = -1000;   // row exponent of an all-zero row
 
@@ -209,8 +209,28 @@ struct TcLinArgs {
   float* C;
   const int* E;         // row exponents of A, [n_nodes, rows_per_node]
   int ldc, n_nodes, rows_per_node, accumulate, nblocks, n_tiles, swizzle;
+  long long* trace;     // optional timeline of CTA 0 (tools/tc_trace.py): records {role, event, index, clock64}
+  int trace_cap;
   TcLinBlock blk[kMaxL];
 };
+// timeline events of CTA 0 (a.trace != nullptr): five roles, each traced by ONE thread that keeps its own
+// record counter in a register and stores {event, index, clock64} with plain stores (no atomics: an atomic's
+// round trip would cost more than the stages being measured).  Layout: role r owns records
+// [r * trace_cap / 5, (r + 1) * trace_cap / 5); word 0 of the buffer is unused, counts are in words 1..5.
+#define TC_TRACE(role, ev, idx)                                                                   \
+  do {                                                                                            \
+    if (a.trace != nullptr && blockIdx.x == 0) {                                                  \
+      const int per = a.trace_cap / 5;                                                            \
+      if (trace_n < per) {                                                                        \
+        long long* rec = a.trace + 8 + 3 * ((size_t)(role) * per + trace_n);                      \
+        rec[0] = (ev);                                                                            \
+        rec[1] = (long long)(idx);                                                                \
+        rec[2] = clock64();                                                                       \
+        ++trace_n;                                                                                \
+        a.trace[1 + (role)] = trace_n;                                                            \
+      }                                                                                           \
+    }                                                                                             \
+  } while (0)
 struct TcMaps { CUtensorMap m[kMaxL]; };   // per block: A viewed as (k, component, node), fp32
 
 // explicit shared-space accesses (the ring pointers are computed from an aligned base, which makes the compiler
@@ -248,6 +268,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
   __shared__ uint32_t tmem_base_sh;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int trace_n = 0;
 
   if (warp == 13) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "r"(512u) : "memory");
@@ -295,6 +316,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
           const int s = it % kTcRawStages;
           mbar_wait(&bar_raw_empty[s], ((it / kTcRawStages) & 1) ^ 1);
+          TC_TRACE(0, 0, it);      // A producer: slot free, issuing chunk `it`
           mbar_expect_tx(&bar_raw_full[s], (uint32_t)kTcRawBytes);
           tma_load_3d(smem + kTcRawOff + (size_t)s * kTcRawBytes, &maps.m[b], kc * kTcKC, ci, mt * kTcBM, &bar_raw_full[s]);
         }
@@ -314,6 +336,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
           const int s = it % kTcWStages;
           mbar_wait(&bar_w_empty[s], ((it / kTcWStages) & 1) ^ 1);
+          TC_TRACE(4, 0, it);      // W producer: slot free, issuing
           mbar_expect_tx(&bar_w_full[s], b_bytes);
           bulk_load(smem + kTcWOff + (size_t)s * kTcWBytes, wsrc + (size_t)kc * b_bytes, b_bytes, &bar_w_full[s]);
         }
@@ -338,6 +361,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
       for (int kc = 0; kc < n_kc; ++kc, ++it) {
         const int s = it % kTcRawStages, o = it % kTcOpsStages;
         mbar_wait(&bar_raw_full[s], (it / kTcRawStages) & 1);
+        if (tid == 0) TC_TRACE(1, 0, it);    // transform: raw chunk landed
         const uint32_t raw = smem_u32(smem + kTcRawOff + (size_t)s * kTcRawBytes + (size_t)r * 128);
         float4 v[4];
 #pragma unroll
@@ -345,6 +369,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         const float dep = (v[0].x + v[1].x) + (v[2].x + v[3].x);   // touches every load: all four have returned
         mbar_arrive_after(&bar_raw_empty[s], dep);                  // the raw chunk is in registers: its slot can be refilled
         mbar_wait(&bar_ops_empty[o], ((it / kTcOpsStages) & 1) ^ 1);
+        if (tid == 0) TC_TRACE(1, 1, it);    // transform: operand slot free
         const uint32_t a0 = smem_u32(smem + kTcOpsOff + (size_t)o * kTcOpsBytes);
         const uint32_t a1 = a0 + kTcASliceBytes, a2 = a1 + kTcASliceBytes;
 #pragma unroll
@@ -371,6 +396,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
           sts128(a2 + off, p2[0], p2[1], p2[2], p2[3]);
         }
         fence_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        if (tid == 0) TC_TRACE(1, 2, it);    // transform: slices written
         mbar_arrive(&bar_ops_full[o]);
       }
     }
@@ -385,6 +411,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         const int n_kc = B.K / kTcKC;
         const int buf = tile_it & 1;
         mbar_wait(&bar_acc_empty[buf], ((tile_it >> 1) & 1) ^ 1);
+        TC_TRACE(2, 2, tile_it);   // MMA: accumulator buffer free
         tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 * kTcMaxNT)   /* fixed halves: tiles of different NT alternate */;
         const uint32_t acc1 = acc0 + (uint32_t)B.NT;
@@ -393,7 +420,9 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
           const int o = it % kTcOpsStages, w = it % kTcWStages;
           mbar_wait(&bar_w_full[w], (it / kTcWStages) & 1);
+          TC_TRACE(2, 0, it);      // MMA: weights landed
           mbar_wait(&bar_ops_full[o], (it / kTcOpsStages) & 1);
+          TC_TRACE(2, 1, it);      // MMA: operands ready, issuing
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + kTcOpsOff + (size_t)o * kTcOpsBytes);
           const uint32_t sb = smem_u32(smem + kTcWOff + (size_t)w * kTcWBytes);
@@ -423,7 +452,7 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
   } else if (warp < 12) {
     // =================== epilogue (warps 8..11 <-> TMEM lanes 32*(warp-8) ..) ===================
     const int ew = warp - 8;
-    const uint32_t scratch = smem_u32(smem + kTcEpiOff) + (uint32_t)ew * (32 * 33 * 4);
+    const uint32_t scratch = smem_u32(smem + kTcEpiOff) + (uint32_t)ew * (32 * 36 * 4);
     uint32_t tile_it = 0;
     int Ea_next = row_exp(blockIdx.x, ew * 32 + lane);
     for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x, ++tile_it) {
@@ -439,13 +468,21 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
       const int node0 = mt * kTcBM + ew * 32;
       const int n_rows = min(32, a.n_nodes - node0);                // rows of this warp that exist (<= 0: none)
       float* cbase = a.C + (size_t)node0 * a.ldc + B.c_off + (size_t)ci * B.c_cs + col0;
+      // One 32 x 32 slab at a time: thread = TMEM lane = row writes its 32 values as 8 x STS.128 into a
+      // [32][36]-float scratch (conflict-free), then the warp re-reads it as 4 rows x 8 column quads per pass
+      // (LDS.128) and writes C with 128-bit stores -- or 128-bit fire-and-forget reductions for C += ...:
+      // every element of C belongs to exactly one tile, so the single add per element is deterministic and no
+      // load latency enters the epilogue.
+      const int rsub = lane >> 3, g4 = (lane & 7) * 4;
       bool waited = false;
       for (int c = 0; c < B.NT; c += 32) {
-        const int cc = c + lane;                                    // this lane's column of the slab
-        const bool col_ok = cc < B.NT && col0 + cc < B.N;          // the last column tile may be padded
-        const float fb = col_ok ? __ldg(B.fb + col0 + cc) : 0.0f;
+        const int cc = c + g4;                                      // first of this lane's 4 columns
+        const bool col_ok = cc < B.NT && col0 + cc < B.N;           // quads are all-in or all-out (NT, N multiples of 4)
+        float4 fb4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) fb4 = __ldg(reinterpret_cast<const float4*>(B.fb + col0 + cc));
         if (!waited) {
           mbar_wait(&bar_acc_full[buf], (tile_it >> 1) & 1);
+          if (tid == 256) TC_TRACE(3, 0, tile_it);    // epilogue: accumulators complete
           tc_fence_after();
           waited = true;
         }
@@ -455,26 +492,39 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
           tmem_ld32(lane_base + (uint32_t)(B.NT + c), v1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            sts32(scratch + (uint32_t)(lane * 33 + j) * 4, (__uint_as_float(v0[j]) + __uint_as_float(v1[j])) * fa);
+          for (int q = 0; q < 8; ++q) {
+            const float x0 = (__uint_as_float(v0[4 * q + 0]) + __uint_as_float(v1[4 * q + 0])) * fa;
+            const float x1 = (__uint_as_float(v0[4 * q + 1]) + __uint_as_float(v1[4 * q + 1])) * fa;
+            const float x2 = (__uint_as_float(v0[4 * q + 2]) + __uint_as_float(v1[4 * q + 2])) * fa;
+            const float x3 = (__uint_as_float(v0[4 * q + 3]) + __uint_as_float(v1[4 * q + 3])) * fa;
+            sts128(scratch + (uint32_t)(lane * 36 + 4 * q) * 4, __float_as_uint(x0), __float_as_uint(x1), __float_as_uint(x2), __float_as_uint(x3));
+          }
         }
         __syncwarp();
         if (col_ok) {
-          // C = v, or C += v as a fire-and-forget reduction (RED.ADD.F32): every element of C belongs to exactly
-          // one tile, so the single add per element is deterministic and no load latency enters the epilogue
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            if (rr < n_rows) {
-              const float v = lds32(scratch + (uint32_t)(rr * 33 + lane) * 4) * fb;
-              float* p = cbase + (size_t)rr * a.ldc + cc;
-              if (a.accumulate) atomicAdd(p, v);
-              else *p = v;
+          float4 vals[8];
+#pragma unroll
+          for (int p8 = 0; p8 < 8; ++p8) vals[p8] = lds128(scratch + (uint32_t)((p8 * 4 + rsub) * 36 + g4) * 4);
+          float* p = cbase + (size_t)rsub * a.ldc + cc;
+          const size_t step = (size_t)4 * a.ldc;
+          if (a.accumulate) {
+#pragma unroll
+            for (int p8 = 0; p8 < 8; ++p8) {
+              if (p8 * 4 + rsub < n_rows)
+                atomicAdd(reinterpret_cast<float4*>(p + p8 * step), make_float4(vals[p8].x * fb4.x, vals[p8].y * fb4.y, vals[p8].z * fb4.z, vals[p8].w * fb4.w));
+            }
+          } else {
+#pragma unroll
+            for (int p8 = 0; p8 < 8; ++p8) {
+              if (p8 * 4 + rsub < n_rows)
+                *reinterpret_cast<float4*>(p + p8 * step) = make_float4(vals[p8].x * fb4.x, vals[p8].y * fb4.y, vals[p8].z * fb4.z, vals[p8].w * fb4.w);
             }
           }
         }
         __syncwarp();
       }
       tc_fence_before();
+      if (tid == 256) TC_TRACE(3, 1, tile_it);        // epilogue: tile written
       mbar_arrive(&bar_acc_empty[buf]);
     }
   }

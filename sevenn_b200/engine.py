@@ -49,7 +49,7 @@ class S7bModelDesc(ctypes.Structure):
 EXPORTS = [
     's7b_last_error', 's7b_version', 's7b_set_option', 's7b_dense_linear', 's7b_engine_create', 's7b_engine_destroy',
     's7b_engine_set_atomic_virial', 's7b_tc_pack_weights', 's7b_gather_rows', 's7b_scatter_add_rows',
-    's7b_engine_set_interior', 's7b_block_linear', 's7b_engine_neighbor_rows_host',
+    's7b_engine_set_interior', 's7b_block_linear', 's7b_tc_trace_enable', 's7b_engine_neighbor_rows_host',
     's7b_d3_create', 's7b_d3_destroy', 's7b_d3_set_params', 's7b_d3_set_damping', 's7b_d3_set_system', 's7b_d3_run_stage',
     's7b_d3_buffer', 's7b_d3_results_host', 's7b_d3_compute_host', 'pair_init', 'pair_set_atom', 'pair_set_domain',
     'pair_run_settings', 'pair_run_coeff', 'pair_run_compute', 'pair_get_energy', 'pair_get_force', 'pair_get_stress', 'pair_fin',
@@ -84,6 +84,7 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_scatter_add_rows.argtypes = [vp, i32, vp, i64, i32, vp, vp]
     lib.s7b_engine_set_interior.argtypes = [vp, i32]
     lib.s7b_engine_neighbor_rows_host.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, ctypes.POINTER(i64), vp]
+    lib.s7b_tc_trace_enable.argtypes = [i32, ctypes.POINTER(vp)]
     lib.s7b_block_linear.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, i32, vp]
     f64 = ctypes.c_double
     lib.s7b_d3_create.argtypes = [ctypes.POINTER(vp)]
