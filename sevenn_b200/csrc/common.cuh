@@ -44,6 +44,8 @@ struct ConvArgs {
   int n_begin, n_dst;        // centre atoms [n_begin, n_dst) of this launch (multi-GPU: interior / boundary ranges)
   int dim_x, dim_mid, w_numel, ny_stride;
   float inv_h;                // 1 / table interval
+  unsigned int* row_max;      // optional [n_dst, rows_per_node]: running max |out| bits of every (l3, k) row of the mid
+  int rows_per_node;          // features (row l3^2 + k), for the tensor-core linear that consumes them (tc_gemm.cuh)
 };
 
 }  // namespace s7b

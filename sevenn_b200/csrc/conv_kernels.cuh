@@ -120,6 +120,7 @@ template <> struct VT<V2> {
   static __device__ __forceinline__ V2 load(const float* p) { return ldg2(p); }
   static __device__ __forceinline__ void store(float* p, V2 v) { *reinterpret_cast<float2*>(p) = v; }
   static __device__ __forceinline__ float hsum(V2 v) { return v.x + v.y; }
+  static __device__ __forceinline__ float amax(V2 v) { return fmaxf(fabsf(v.x), fabsf(v.y)); }
   // cubic coefficients of the channel pair starting at (even) column c of table row tk
   static __device__ __forceinline__ void coef(const ConvArgs& a, int tk, int c, V2& a0, V2& a1, V2& a2, V2& a3) {
     const size_t ti = (size_t)tk * (a.w_numel >> 1) + (c >> 1);
@@ -137,6 +138,7 @@ template <> struct VT<float> {
   static __device__ __forceinline__ float load(const float* p) { return __ldg(p); }
   static __device__ __forceinline__ void store(float* p, float v) { *p = v; }
   static __device__ __forceinline__ float hsum(float v) { return v; }
+  static __device__ __forceinline__ float amax(float v) { return fabsf(v); }
   static __device__ __forceinline__ void coef(const ConvArgs& a, int tk, int c, float& a0, float& a1, float& a2, float& a3) {
     const size_t ti = (size_t)tk * (a.w_numel >> 1) + (c >> 1);
     const float4 c01 = __ldg(a.table + ti);
@@ -226,6 +228,29 @@ conv_fwd_kernel(const ConvArgs a, const ConvRole role, float* __restrict__ out) 
     }
   }
 
+  // row maxima of the mid features for the tensor-core self_interaction_2 (fixed-point row scaling): one
+  // group reduction and one atomicMax per (l3, k) row this role contributes to -- saves a pass over the mid tensor
+  if (a.row_max != nullptr) {
+#pragma unroll
+    for (int l3 = 0; l3 < kMaxL; ++l3) {
+      bool present = false;
+#pragma unroll
+      for (int p = 0; p < Kind::NPATH; ++p) present = present || (Kind::path_l3(p) == l3);
+      if (!present) continue;
+#pragma unroll
+      for (int k = 0; k < 2 * l3 + 1; ++k) {
+        float mx = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NV; ++c)
+#pragma unroll
+          for (int p = 0; p < Kind::NPATH; ++p)
+            if (Kind::path_l3(p) == l3) mx = fmaxf(mx, VT<V>::amax(acc[c][Kind::acc_off(p) + k]));
+#pragma unroll
+        for (int off = LPN / 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (m.node_ok && m.sl == 0) atomicMax(a.row_max + (size_t)m.n * a.rows_per_node + l3 * l3 + k, __float_as_uint(mx));
+      }
+    }
+  }
   if (!m.node_ok) return;
   float* __restrict__ orow = out + (size_t)m.n * a.dim_mid;
 #pragma unroll

@@ -146,6 +146,7 @@ struct LayerCfg {
 struct RowExp {
   DevBuf buf;
   int rows_per_node = 0;
+  bool bits = false;      // raw |a|-maximum bits (filled by the producer kernel) instead of exponents
 };
 
 }  // namespace s7b
@@ -468,6 +469,7 @@ static int launch_row_exponents(RowExp& re, const float* A, int lda, const int* 
   }
   r.rows_per_node = rows;
   re.rows_per_node = rows;
+  re.bits = false;
   if (rows == 0 || n_nodes == 0) return 0;
   if (re.buf.ensure((size_t)n_nodes * rows * sizeof(int))) return fail("cudaMalloc failed for row exponents");
   r.E = re.buf.as<int>();
@@ -499,6 +501,7 @@ static int launch_tc_linear(const TcWeights& w, const RowExp& re, const float* A
   t.rows_per_node = re.rows_per_node;
   t.accumulate = accumulate ? 1 : 0;
   t.swizzle = g_opt_tc_swizzle;
+  t.e_bits = re.bits ? 1 : 0;
   t.trace = g_tc_trace;
   t.trace_cap = g_tc_trace_cap;
   const int n_mt = (n_nodes + kTcBM - 1) / kTcBM;
@@ -1090,6 +1093,15 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
       if (stage == S7B_STAGE_FWD_CONV_INTERIOR) ca.n_dst = e->n_interior;
       if (stage == S7B_STAGE_FWD_LAYER_A2) ca.n_begin = e->n_interior;
+      // the convolution kernels also leave the row maxima of `mid` for the tensor-core self_interaction_2
+      const bool fused_rows = g_opt_tc_gemm && L.tcw.count("si2") && L.tcw.at("si2") && L.tcw.at("si2")->ok;
+      if (fused_rows) {
+        e->re_mid.rows_per_node = L.n_lg * L.n_lg;
+        e->re_mid.bits = true;
+        if (head) S7B_CUDA_CHECK(cudaMemsetAsync(e->re_mid.buf.p, 0, (size_t)Nl * e->re_mid.rows_per_node * sizeof(int), st));
+        ca.row_max = e->re_mid.buf.as<unsigned int>();
+        ca.rows_per_node = e->re_mid.rows_per_node;
+      }
       {
         const bool par = e->concurrent && g_opt_concurrent && !e->prof.enabled && L.n_lx > 1;
         if (par) S7B_CUDA_CHECK(cudaEventRecord(e->ev_fork, st));
@@ -1110,7 +1122,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       if (require(si2, "si2")) return 1;
       {
         ProfScope ps(e->prof, st, "si2_gemm", t);
-        if (node_linear(L, "si2", e->re_mid, true, L.n_lg, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st)) return 1;
+        if (node_linear(L, "si2", e->re_mid, !fused_rows, L.n_lg, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st)) return 1;
       }
       // gate
       {

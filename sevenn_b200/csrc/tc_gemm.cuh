@@ -169,7 +169,8 @@ struct RowExpArgs {
 
 __global__ void row_exponent_kernel(const RowExpArgs a) {
   // one warp per node: the node's row is read once, coalesced (float4 per lane); every float4 lies inside one
-  // (block, component) row (K is a multiple of 4), whose running maximum is kept in shared memory
+  // (block, component) row (K is a multiple of 4).  Lanes that hold quads of the same row combine their maxima
+  // with one warp reduction (match.any + redux.sync), its leader updates the row's slot in shared memory.
   __shared__ unsigned int smax[8][16];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -179,13 +180,22 @@ __global__ void row_exponent_kernel(const RowExpArgs a) {
     for (int b = 0; b < a.nblocks; ++b) {
       const int K = a.K[b], quads = (a.d[b] * K) >> 2;
       const float4* row = reinterpret_cast<const float4*>(a.A + (size_t)n * a.lda + a.a_off[b]);
-      for (int q = lane; q < quads; q += 32) {
-        const float4 v = __ldg(row + q);
-        unsigned int m = __float_as_uint(v.x) & 0x7fffffffu;
-        m = max(m, __float_as_uint(v.y) & 0x7fffffffu);
-        m = max(m, __float_as_uint(v.z) & 0x7fffffffu);
-        m = max(m, __float_as_uint(v.w) & 0x7fffffffu);
-        atomicMax(&smax[wib][a.row_base[b] + (4 * q) / K], m);
+      for (int q0 = 0; q0 < quads; q0 += 32) {
+        const int q = q0 + lane;
+        unsigned int m = 0u;
+        int r = -1;
+        if (q < quads) {
+          const float4 v = __ldg(row + q);
+          m = __float_as_uint(v.x) & 0x7fffffffu;
+          m = max(m, __float_as_uint(v.y) & 0x7fffffffu);
+          m = max(m, __float_as_uint(v.z) & 0x7fffffffu);
+          m = max(m, __float_as_uint(v.w) & 0x7fffffffu);
+          r = a.row_base[b] + (4 * q) / K;
+        }
+        const unsigned int peers = __match_any_sync(0xffffffffu, r);
+        const unsigned int mm = __reduce_max_sync(peers, m);
+        if (r >= 0 && lane == __ffs(peers) - 1) smax[wib][r] = max(smax[wib][r], mm);
+        __syncwarp();
       }
     }
   }
@@ -209,6 +219,7 @@ struct TcLinArgs {
   float* C;
   const int* E;         // row exponents of A, [n_nodes, rows_per_node]
   int ldc, n_nodes, rows_per_node, accumulate, nblocks, n_tiles, swizzle;
+  int e_bits;           // E holds the raw maxima (|a| bits, written by the producer kernel) instead of exponents
   long long* trace;     // optional timeline of CTA 0 (tools/tc_trace.py): records {role, event, index, clock64}
   int trace_cap;
   TcLinBlock blk[kMaxL];
@@ -302,7 +313,13 @@ blocklin_tc_kernel(const TcLinArgs a, const __grid_constant__ TcMaps maps) {
     int b, mt, ci, nt;
     decode(t, b, mt, ci, nt);
     const int node = mt * kTcBM + row;
-    return node < a.n_nodes ? __ldg(a.E + (size_t)node * a.rows_per_node + a.blk[b].row_base + ci) : kTcZeroRow;
+    if (node >= a.n_nodes) return kTcZeroRow;
+    int v = __ldg(a.E + (size_t)node * a.rows_per_node + a.blk[b].row_base + ci);
+    if (a.e_bits) {
+      const int ex = v >> 23;
+      v = (ex < 30 || ex == 255) ? kTcZeroRow : ex - 126;          // |a| < 2^(ex-126)
+    }
+    return v;
   };
 
   if (warp == 12) {
