@@ -1125,9 +1125,18 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         if (node_linear(L, "si2", e->re_mid, !fused_rows, L.n_lg, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, e->g[t].as<float>(), L.dim_g, L.g_off, L.g_muls, L.n_lg, si2, Nl, true, st)) return 1;
       }
       // gate
+      // gate; with the tensor-core linears the kernel also leaves the row exponents of h for self_interaction_1 / sc
+      const bool h_rows = g_opt_tc_gemm && t + 1 < T && e->layers[t + 1].tcw.count("si1") && e->layers[t + 1].tcw.at("si1") &&
+                          e->layers[t + 1].tcw.at("si1")->ok && L.n_lg * L.n_lg <= 16;
       {
         ProfScope ps(e->prof, st, "gate_fwd", t);
-        gate_fwd_kernel<<<grid1d((size_t)Nl * L.dim_h, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->h.as<float>(), Nl);
+        if (h_rows) {
+          e->re_h.rows_per_node = L.n_lg * L.n_lg;
+          e->re_h.bits = false;
+          gate_fwd_rows_kernel<<<(Nl + 7) / 8, 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->h.as<float>(), Nl, e->re_h.buf.as<int>(), e->re_h.rows_per_node, kTcZeroRow);
+        } else {
+          gate_fwd_kernel<<<grid1d((size_t)Nl * L.dim_h, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->h.as<float>(), Nl);
+        }
         S7B_LAUNCH_CHECK();
       }
       if (t + 1 < T) {
@@ -1136,7 +1145,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
         if (require(si1, "si1")) return 1;
         ProfScope ps(e->prof, st, "si1_gemm", t + 1);
         // self_interaction_1 of the next layer -> local rows of x[t+1] (ghost rows: caller's exchange)
-        if (node_linear(N, "si1", e->re_h, true, N.n_lx, e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st)) return 1;
+        if (node_linear(N, "si1", e->re_h, !h_rows, N.n_lx, e->h.as<float>(), N.dim_x, N.x_off, N.x_muls, e->x[t + 1].as<float>(), N.dim_x, N.x_off, N.x_muls, N.n_lx, si1, Nl, false, st)) return 1;
       }
       if (stage != S7B_STAGE_FWD_LAYER) return 0;
     }
@@ -1177,16 +1186,23 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       if (head && t > 0 && Nn > 0) S7B_CUDA_CHECK(cudaMemsetAsync(e->dx.p, 0, (size_t)Nn * L.dim_x * sizeof(float), st));
       if (Nl == 0) return 0;
       if (head) {
+        const bool dg_rows = g_opt_tc_gemm && L.tcw.count("si2T") && L.tcw.at("si2T") && L.tcw.at("si2T")->ok && L.n_lg * L.n_lg <= 16;
         {
           ProfScope ps(e->prof, st, "gate_bwd", t);
-          gate_bwd_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl);
+          if (dg_rows) {      // ... and the row exponents of dg for si2^T / sc^T
+            e->re_dg.rows_per_node = L.n_lg * L.n_lg;
+            e->re_dg.bits = false;
+            gate_bwd_rows_kernel<<<(Nl + 7) / 8, 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl, e->re_dg.buf.as<int>(), e->re_dg.rows_per_node, kTcZeroRow);
+          } else {
+            gate_bwd_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl);
+          }
           S7B_LAUNCH_CHECK();
         }
         const float* si2T = lparam(e, t, "si2T");
         if (require(si2T, "si2T")) return 1;
         // d(mid) = dg * si2^T
         ProfScope ps(e->prof, st, "si2T_gemm", t);
-        if (node_linear(L, "si2T", e->re_dg, true, L.n_lg, e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st)) return 1;
+        if (node_linear(L, "si2T", e->re_dg, !dg_rows, L.n_lg, e->dg.as<float>(), L.dim_g, L.g_off, L.g_muls, e->mid.as<float>(), L.dim_mid, L.mid_off, L.mid_K, L.n_lg, si2T, Nl, false, st)) return 1;
       }
       if (E > 0) {
         ConvArgs ca = make_conv_args(e, t, e->x[t].as<float>());
