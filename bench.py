@@ -296,7 +296,7 @@ def run_engine(args):
         part = brick_decompose(pos, cell, species_all, GRIDS[args.gpus], rank, 5.0)
         n_edges_local = part['edge_index'].shape[1]
         eng = B200Engine(meta, arrays, radial=args.radial, device=local_rank)
-        runner = DistributedRunner(eng, part, cuda_graph=bool(int(os.environ.get('S7B_CUDA_GRAPH', '1'))))
+        runner = DistributedRunner(eng, part)      # per-stage CUDA graphs; S7B_CUDA_GRAPH=1 opts into whole-step capture
         t = torch.tensor([n_edges_local], device=dev, dtype=torch.int64)
         dist.all_reduce(t)
         n_edges = int(t.item())
@@ -428,8 +428,8 @@ def run_engine(args):
                 'parallelism': 'single GPU' if world == 1 else f'spatial bricks {GRIDS[args.gpus]} + NCCL ghost exchange',
                 'l2': 'flushed with a 256 MiB write between timed steps',
                 'cuda_graph': (bool(int(os.environ.get('S7B_CUDA_GRAPH', '1'))) and args.radial == 'table') if world == 1
-                else bool(runner.use_graph and runner.graph_replays > 0),
-                'cuda_graph_note': None if world == 1 else (runner.graph_error or f'{runner.graph_captures} capture(s), {runner.graph_replays} replays; NCCL calls inside the graph'),
+                else ('whole step' if (runner.use_graph and runner.graph_replays > 0) else ('per stage' if runner.stage_graphs else False)),
+                'cuda_graph_note': None if world == 1 else (runner.graph_error or 'stage graphs (captures, replays) = %s; NCCL calls between the graphs' % (eng.stage_graph_stats(),)),
                 'tc_gemm': bool(int(os.environ.get('S7B_TC_GEMM', '1'))),
                 'energy_eV': float(out[0]) if world == 1 else float(out['energy'])},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},

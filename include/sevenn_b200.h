@@ -213,6 +213,12 @@ S7B_API int64_t s7b_launch_count(int reset);
 /* How often s7b_engine_compute captured a new CUDA graph / replayed one (either pointer may be NULL). */
 S7B_API int s7b_engine_graph_stats(S7bEngine* eng, int64_t* captures, int64_t* replays);
 
+/* With s7b_set_option("stage_graphs", 1), s7b_engine_run_stage captures each (stage, layer) into its own CUDA
+ * graph on first use and replays it on the caller's stream afterwards (table radial mode, not under
+ * profiling, not while the caller's stream is itself capturing).  Meant for callers that put their own
+ * work -- the ghost exchanges of the multi-GPU runner -- between the stages.  Captures / replays so far: */
+S7B_API int s7b_engine_stage_graph_stats(S7bEngine* eng, int64_t* captures, int64_t* replays);
+
 /* ---- operator-level plug-in: fused gather -> 'uvu' tensor product -> scatter ------------- */
 /* irreps of x as multiplicities per l (even parity), filter lmax, and lmax of the output; the
  * instruction set is the complete triangle-allowed one of sevenn/nn/convolution.py:61-82.      */

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -197,6 +198,16 @@ struct S7bEngine {
   std::vector<int64_t> g_key;
   int64_t g_launches_per_replay = 0;
   int64_t g_captures = 0, g_replays = 0;
+  // one graph per (stage, layer) for callers that drive the stages themselves (multi-GPU runner, LAMMPS front-ends)
+  struct StageGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<int64_t> key;
+    int64_t launches = 0, replays_since_capture = 0;
+    int thrash = 0;                       // re-captures that were replayed fewer than twice
+  };
+  std::map<int, StageGraph> stage_graphs;
+  bool capturing = false;
+  int64_t sg_captures = 0, sg_replays = 0;
 };
 
 struct S7bConvPlan {
@@ -311,6 +322,7 @@ static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* 
 
 static int g_opt_atomic_virial = 0;   // engines created afterwards also produce the per-atom virial
 static int g_opt_concurrent = 1;   // co-schedule the per-l1 convolution kernels of a layer on side streams
+static int g_opt_stage_graphs = 0;  // s7b_engine_run_stage replays one captured graph per (stage, layer)
 static int g_opt_cuda_graph = 1;   // s7b_engine_compute replays a captured CUDA graph of the step (table mode)
 static int g_opt_tc_gemm = 1;   // 1 (default): node linears on tcgen05 (error-free bf16x3 slices, tc_gemm.cuh); 0: FP32 SIMT
 static long long* g_tc_trace = nullptr;   // device buffer [1 + 4 * cap] when s7b_tc_trace_enable was called (debug)
@@ -459,7 +471,7 @@ static int launch_row_exponents(RowExp& re, const float* A, int lda, const int* 
   int rows = 0;
   for (int l = 0; l < n_l; ++l) {
     if (a_K[l] == 0) continue;
-    if (a_K[l] % 4 != 0) return fail("row exponents need K % 4 == 0");
+    if (a_K[l] % 32 != 0) return fail("row exponents need K % 32 == 0");
     const int b = r.nblocks++;
     r.d[b] = 2 * l + 1;
     r.K[b] = a_K[l];
@@ -661,6 +673,7 @@ int s7b_set_option(const char* name, int value) {
   if (std::string(name) == "atomic_virial") { g_opt_atomic_virial = value; return 0; }
   if (std::string(name) == "concurrent_conv") { g_opt_concurrent = value; return 0; }
   if (std::string(name) == "cuda_graph") { g_opt_cuda_graph = value; return 0; }
+  if (std::string(name) == "stage_graphs") { g_opt_stage_graphs = value; return 0; }
   return fail(std::string("unknown option: ") + name);
 }
 
@@ -836,6 +849,7 @@ void s7b_engine_destroy(S7bEngine* e) {
   }
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->gexec) cudaGraphExecDestroy(e->gexec);
+  for (auto& kv : e->stage_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (e->gstream) cudaStreamDestroy(e->gstream);
   if (e->g_in) cudaEventDestroy(e->g_in);
   if (e->g_out) cudaEventDestroy(e->g_out);
@@ -1025,8 +1039,7 @@ static int require(const void* p, const char* what) {
   return fail(std::string("missing parameter: ") + what);
 }
 
-int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
-  if (!e) return fail("null engine");
+static int run_stage_impl(S7bEngine* e, int stage, int t, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int T = e->desc.n_layers;
   const int Nn = e->n_nodes, Nl = e->n_local;
@@ -1191,8 +1204,9 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
           ProfScope ps(e->prof, st, "gate_bwd", t);
           if (dg_rows) {      // ... and the row exponents of dg for si2^T / sc^T
             e->re_dg.rows_per_node = L.n_lg * L.n_lg;
-            e->re_dg.bits = false;
-            gate_bwd_rows_kernel<<<(Nl + 7) / 8, 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl, e->re_dg.buf.as<int>(), e->re_dg.rows_per_node, kTcZeroRow);
+            e->re_dg.bits = true;
+            S7B_CUDA_CHECK(cudaMemsetAsync(e->re_dg.buf.p, 0, (size_t)Nl * e->re_dg.rows_per_node * sizeof(int), st));
+            gate_bwd_rows_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl, e->re_dg.buf.as<unsigned int>(), e->re_dg.rows_per_node);
           } else {
             gate_bwd_kernel<<<grid1d((size_t)Nl * L.dim_g, 256), 256, 0, st>>>(L.gate, e->g[t].as<float>(), e->dh.as<float>(), e->dg.as<float>(), Nl);
           }
@@ -1283,17 +1297,88 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
   }
 }
 
+// everything a captured graph bakes in: sizes, edge capacity, graph-array pointers, any (re)allocation, the options
+static std::vector<int64_t> graph_key(const S7bEngine* e) {
+  return {e->n_nodes, e->n_local, e->n_interior, e->E_cap, e->n_edges > 0 ? 1 : 0, (int64_t)(uintptr_t)e->d_species,
+          (int64_t)(uintptr_t)e->d_rowptr, (int64_t)(uintptr_t)e->d_src, (int64_t)(uintptr_t)e->d_edge_vec,
+          g_alloc_gen, g_opt_concurrent, g_opt_tc_gemm + 2 * g_opt_tc_swizzle, e->concurrent ? 1 : 0,
+          e->want_atomic_virial ? 1 : 0};
+}
+
+static int ensure_graph_stream(S7bEngine* e) {
+  if (e->gstream) return 0;
+  S7B_CUDA_CHECK(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
+  S7B_CUDA_CHECK(cudaEventCreateWithFlags(&e->g_in, cudaEventDisableTiming));
+  S7B_CUDA_CHECK(cudaEventCreateWithFlags(&e->g_out, cudaEventDisableTiming));
+  return 0;
+}
+
+// capture fn(gstream) into an executable graph; *launches = kernels recorded
+static int capture_graph(S7bEngine* e, const std::function<int(cudaStream_t)>& fn, cudaGraphExec_t* exec, int64_t* launches) {
+  const int64_t before = g_launches + g_conv_launches;
+  S7B_CUDA_CHECK(cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal));
+  e->capturing = true;
+  const int rc = fn(e->gstream);
+  e->capturing = false;
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
+  *launches = g_launches + g_conv_launches - before;
+  g_launches -= *launches;                 // recorded, not launched
+  if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(std::string("CUDA graph capture failed: ") + cudaGetErrorString(ce)); }
+  const cudaError_t ci = cudaGraphInstantiate(exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ci != cudaSuccess) { *exec = nullptr; cudaGetLastError(); return fail(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ci)); }
+  return 0;
+}
+
+// A caller that drives the stages itself (multi-GPU runner: ghost exchanges between the stages; LAMMPS
+// front-ends) cannot replay the whole step as one graph, but every stage between two exchanges still is a
+// fixed launch sequence: with option "stage_graphs" each (stage, layer) is captured once and replayed on the
+// caller's stream -- ~22 graph launches per step instead of ~170 kernel launches.  An entry whose key keeps
+// changing (positions-in MD: new graph arrays every step) stops capturing after three wasted captures.
+int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
+  if (!e) return fail("null engine");
+  const bool table = e->desc.table_knots > 0;
+  if (!g_opt_stage_graphs || e->capturing || !table || e->prof.enabled || !e->radial_ready)
+    return run_stage_impl(e, stage, t, stream);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return run_stage_impl(e, stage, t, stream); }
+  if (cs != cudaStreamCaptureStatusNone) return run_stage_impl(e, stage, t, stream);    // the caller is capturing already
+  S7bEngine::StageGraph& sg = e->stage_graphs[stage * 64 + t];
+  if (sg.thrash >= 3) return run_stage_impl(e, stage, t, stream);
+  const std::vector<int64_t> key = graph_key(e);
+  if (!sg.exec || key != sg.key) {
+    if (sg.exec) {
+      cudaGraphExecDestroy(sg.exec);
+      sg.exec = nullptr;
+      if (sg.replays_since_capture < 2 && ++sg.thrash >= 3) return run_stage_impl(e, stage, t, stream);
+    }
+    if (ensure_graph_stream(e)) return 1;
+    if (capture_graph(e, [&](cudaStream_t s) { return run_stage_impl(e, stage, t, s); }, &sg.exec, &sg.launches)) return 1;
+    sg.key = key;
+    sg.replays_since_capture = 0;
+    ++e->sg_captures;
+  }
+  S7B_CUDA_CHECK(cudaGraphLaunch(sg.exec, st));
+  g_launches += sg.launches;
+  ++sg.replays_since_capture;
+  ++e->sg_replays;
+  return 0;
+}
+
 static int run_all_stages(S7bEngine* e, void* stream) {
   const int T = e->desc.n_layers;
-  if (s7b_engine_run_stage(e, S7B_STAGE_FWD_BEGIN, 0, stream)) return 1;
+  if (run_stage_impl(e, S7B_STAGE_FWD_BEGIN, 0, stream)) return 1;
   for (int t = 0; t < T; ++t)
-    if (s7b_engine_run_stage(e, S7B_STAGE_FWD_LAYER, t, stream)) return 1;
-  if (s7b_engine_run_stage(e, S7B_STAGE_FWD_END, 0, stream)) return 1;
+    if (run_stage_impl(e, S7B_STAGE_FWD_LAYER, t, stream)) return 1;
+  if (run_stage_impl(e, S7B_STAGE_FWD_END, 0, stream)) return 1;
   for (int t = T - 1; t >= 0; --t) {
-    if (s7b_engine_run_stage(e, S7B_STAGE_BWD_LAYER_A, t, stream)) return 1;
-    if (t > 0 && s7b_engine_run_stage(e, S7B_STAGE_BWD_LAYER_B, t, stream)) return 1;
+    if (run_stage_impl(e, S7B_STAGE_BWD_LAYER_A, t, stream)) return 1;
+    if (t > 0 && run_stage_impl(e, S7B_STAGE_BWD_LAYER_B, t, stream)) return 1;
   }
-  return s7b_engine_run_stage(e, S7B_STAGE_BWD_END, 0, stream);
+  return run_stage_impl(e, S7B_STAGE_BWD_END, 0, stream);
 }
 
 // The whole step is ~75 launches; below a few thousand atoms their launch latency, not the kernels, sets
@@ -1308,31 +1393,12 @@ int s7b_engine_compute(S7bEngine* e, void* stream) {
   if (!g_opt_cuda_graph || !table || e->prof.enabled) return run_all_stages(e, stream);
   if (!e->radial_ready) return fail("parameter 'bessel' was not set");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (!e->gstream) {
-    S7B_CUDA_CHECK(cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking));
-    S7B_CUDA_CHECK(cudaEventCreateWithFlags(&e->g_in, cudaEventDisableTiming));
-    S7B_CUDA_CHECK(cudaEventCreateWithFlags(&e->g_out, cudaEventDisableTiming));
-  }
-  const std::vector<int64_t> key = {
-      e->n_nodes, e->n_local, e->E_cap, e->n_edges > 0 ? 1 : 0, (int64_t)(uintptr_t)e->d_species,
-      (int64_t)(uintptr_t)e->d_rowptr, (int64_t)(uintptr_t)e->d_src, (int64_t)(uintptr_t)e->d_edge_vec,
-      g_alloc_gen, g_opt_concurrent, g_opt_tc_gemm + 2 * g_opt_tc_swizzle, e->concurrent ? 1 : 0};
+  if (ensure_graph_stream(e)) return 1;
+  const std::vector<int64_t> key = graph_key(e);
   if (!e->gexec || key != e->g_key) {
     if (e->gexec) { cudaGraphExecDestroy(e->gexec); e->gexec = nullptr; }
-    const int64_t before = g_launches + g_conv_launches;
-    S7B_CUDA_CHECK(cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal));
-    const int rc = run_all_stages(e, e->gstream);
-    cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
-    const int64_t captured = g_launches + g_conv_launches - before;
-    g_launches -= captured;                 // recorded, not launched
-    if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
-    if (ce != cudaSuccess) { cudaGetLastError(); return fail(std::string("CUDA graph capture failed: ") + cudaGetErrorString(ce)); }
-    const cudaError_t ci = cudaGraphInstantiate(&e->gexec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ci != cudaSuccess) { e->gexec = nullptr; cudaGetLastError(); return fail(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ci)); }
+    if (capture_graph(e, [&](cudaStream_t s) { return run_all_stages(e, s); }, &e->gexec, &e->g_launches_per_replay)) return 1;
     e->g_key = key;
-    e->g_launches_per_replay = captured;
     ++e->g_captures;
   }
   S7B_CUDA_CHECK(cudaEventRecord(e->g_in, st));
@@ -1349,6 +1415,13 @@ int s7b_engine_graph_stats(S7bEngine* e, int64_t* captures, int64_t* replays) {
   if (!e) return fail("null engine");
   if (captures) *captures = e->g_captures;
   if (replays) *replays = e->g_replays;
+  return 0;
+}
+
+int s7b_engine_stage_graph_stats(S7bEngine* e, int64_t* captures, int64_t* replays) {
+  if (!e) return fail("null engine");
+  if (captures) *captures = e->sg_captures;
+  if (replays) *replays = e->sg_replays;
   return 0;
 }
 

@@ -225,11 +225,12 @@ __global__ void gate_bwd_kernel(const GateDesc d, const float* __restrict__ g,
 // tensor-core linears that consume it (tc_gemm.cuh: fixed-point row scaling needs max |a| of every (l, component)
 // row): E[n, l^2 + i] = exponent with max |row| < 2^E, or zero_row for an all-zero row.  Lanes walk the node's
 // elements 32 at a time (coalesced); lanes holding elements of the same row combine with match.any + redux.sync.
+// all multiplicities are multiples of 32 (build_layer_cfg), so the 32 consecutive elements of one warp
+// iteration lie in ONE row: a single warp reduction, lane 0 keeps the running maximum
 __device__ __forceinline__ void row_max_update(unsigned int* smax, int r, float v, int lane) {
-  const unsigned int m = __float_as_uint(v) & 0x7fffffffu;
-  const unsigned int peers = __match_any_sync(0xffffffffu, r);
-  const unsigned int mm = __reduce_max_sync(peers, m);
-  if (r >= 0 && lane == __ffs(peers) - 1) smax[r] = max(smax[r], mm);
+  const unsigned int mm = __reduce_max_sync(0xffffffffu, __float_as_uint(v) & 0x7fffffffu);
+  const int rr = __shfl_sync(0xffffffffu, r, 0);
+  if (lane == 0 && rr >= 0) smax[rr] = max(smax[rr], mm);
   __syncwarp();
 }
 __device__ __forceinline__ void row_exponents_store(const unsigned int* smax, int* E, int rows, int lane, int zero_row) {
@@ -272,48 +273,43 @@ __global__ void gate_fwd_rows_kernel(const GateDesc d, const float* __restrict__
   row_exponents_store(smax[wib], E + (size_t)n * rows_per_node, rows_per_node, lane, zero_row);
 }
 
+// dg from dh, one thread per element like gate_bwd_kernel (the gate-scalar elements chain 2l+1 dependent
+// loads: a warp-per-node walk serialises them, one thread per element hides them), plus the row maxima of dg:
+// the 32 elements of a warp lie in one (node, row) -- every multiplicity is a multiple of 32 -- so one warp
+// reduction and one atomicMax on the bit pattern of |v| per warp.  bits [n_nodes, rows_per_node] is zeroed by the caller.
 __global__ void gate_bwd_rows_kernel(const GateDesc d, const float* __restrict__ g, const float* __restrict__ dh,
-                                     float* __restrict__ dg, int n_nodes, int* __restrict__ E, int rows_per_node,
-                                     int zero_row) {
-  __shared__ unsigned int smax[8][16];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (lane < 16) smax[wib][lane] = 0u;
-  __syncwarp();
-  if (n >= n_nodes) return;
-  const float* grow = g + (size_t)n * d.dim_g;
-  const float* hrow = dh + (size_t)n * d.dim_h;
-  float* orow = dg + (size_t)n * d.dim_g;
-  for (int c0 = 0; c0 < d.dim_g; c0 += 32) {
-    const int c = c0 + lane;
-    float v = 0.0f;
-    int r = -1;
-    if (c < d.dim_g) {
-      if (c < d.n_scalars) {
-        v = hrow[c] * dsilu_n(grow[c]);
-        r = 0;
-      } else if (c < d.g_off[1] || d.lmax == 0) {
-        int l = 1;                                        // a gate scalar: find its l
-        while (l < d.lmax && c >= d.gate_off[l + 1]) ++l;
-        const int u = c - d.gate_off[l];
-        float s = 0.0f;
-        for (int i = 0; i < 2 * l + 1; ++i)
-          s = fmaf(hrow[d.h_off[l] + i * d.mul[l] + u], grow[d.g_off[l] + i * d.mul[l] + u], s);
-        v = s * dsilu_n(grow[c]);
-        r = 0;
-      } else {
-        int l = 1;
-        while (l < d.lmax && c >= d.g_off[l + 1]) ++l;
-        const int rel = c - d.g_off[l];
-        const int u = rel % d.mul[l];
-        v = hrow[d.h_off[l] + rel] * silu_n(grow[d.gate_off[l] + u]);
-        r = l * l + rel / d.mul[l];
-      }
-      orow[c] = v;
+                                     float* __restrict__ dg, int n_nodes, unsigned int* __restrict__ bits, int rows_per_node) {
+  const size_t total = (size_t)n_nodes * d.dim_g;
+  const int lane = threadIdx.x & 31;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / d.dim_g), c = (int)(idx - (size_t)n * d.dim_g);
+    const float* grow = g + (size_t)n * d.dim_g;
+    const float* hrow = dh + (size_t)n * d.dim_h;
+    float v;
+    int r = 0;
+    if (c < d.n_scalars) {
+      v = hrow[c] * dsilu_n(grow[c]);
+    } else if (c < d.g_off[1] || d.lmax == 0) {
+      int l = 1;                                        // a gate scalar: find its l
+      while (l < d.lmax && c >= d.gate_off[l + 1]) ++l;
+      const int u = c - d.gate_off[l];
+      float s = 0.0f;
+      for (int i = 0; i < 2 * l + 1; ++i)
+        s = fmaf(hrow[d.h_off[l] + i * d.mul[l] + u], grow[d.g_off[l] + i * d.mul[l] + u], s);
+      v = s * dsilu_n(grow[c]);
+    } else {
+      int l = 1;
+      while (l < d.lmax && c >= d.g_off[l + 1]) ++l;
+      const int rel = c - d.g_off[l];
+      const int u = rel % d.mul[l];
+      v = hrow[d.h_off[l] + rel] * silu_n(grow[d.gate_off[l] + u]);
+      r = l * l + rel / d.mul[l];
     }
-    row_max_update(smax[wib], r, v, lane);
+    dg[idx] = v;
+    const unsigned int mm = __reduce_max_sync(0xffffffffu, __float_as_uint(v) & 0x7fffffffu);
+    if (lane == 0) atomicMax(bits + (size_t)n * rows_per_node + r, mm);
   }
-  row_exponents_store(smax[wib], E + (size_t)n * rows_per_node, rows_per_node, lane, zero_row);
 }
 
 // out[n, :width] = table[idx[n], :width]

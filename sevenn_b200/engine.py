@@ -55,7 +55,7 @@ EXPORTS = [
     'pair_run_settings', 'pair_run_coeff', 'pair_run_compute', 'pair_get_energy', 'pair_get_force', 'pair_get_stress', 'pair_fin',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
     's7b_engine_buffer', 's7b_engine_compute_host', 's7b_engine_set_positions_host',
-    's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_graph_stats', 's7b_engine_set_profiling',
+    's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_graph_stats', 's7b_engine_stage_graph_stats', 's7b_engine_set_profiling',
     's7b_engine_profile_count', 's7b_engine_profile_entry', 's7b_conv_plan_create',
     's7b_conv_plan_destroy', 's7b_conv_plan_dims', 's7b_conv_forward', 's7b_conv_backward',
 ]
@@ -114,6 +114,7 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_launch_count.argtypes = [ctypes.c_int]
     lib.s7b_launch_count.restype = i64
     lib.s7b_engine_graph_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.s7b_engine_stage_graph_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.s7b_conv_plan_create.argtypes = [i32, ctypes.POINTER(i32), i32, i32, ctypes.POINTER(vp)]
     lib.s7b_conv_plan_destroy.argtypes = [vp]
     lib.s7b_conv_plan_destroy.restype = None
@@ -528,6 +529,12 @@ class B200Engine:
         """(captures, replays) of the CUDA-graph path of ``compute``."""
         c, r = ctypes.c_int64(), ctypes.c_int64()
         check(self.lib.s7b_engine_graph_stats(self._h, ctypes.byref(c), ctypes.byref(r)))
+        return int(c.value), int(r.value)
+
+    def stage_graph_stats(self):
+        """(captures, replays) of the per-stage CUDA graphs of ``run_stage`` (option ``stage_graphs``)."""
+        c, r = ctypes.c_int64(), ctypes.c_int64()
+        check(self.lib.s7b_engine_stage_graph_stats(self._h, ctypes.byref(c), ctypes.byref(r)))
         return int(c.value), int(r.value)
 
     def launch_count(self, reset: bool = False) -> int:

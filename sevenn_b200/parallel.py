@@ -21,8 +21,10 @@ between.  Here:
   split at that point: the interior part of layer t runs while the ghost rows of x(t) are still in
   flight, and in the backward the boundary part runs first so that the ghost rows of dx(t) travel
   while the interior part is computed (stages 10-13 of ``include/sevenn_b200.h``);
-* on CUDA the whole step -- kernels, pack/unpack and the NCCL calls -- is captured once into a CUDA
-  graph and replayed (``cuda_graph``), so the per-step host cost is one graph launch;
+* on CUDA every stage between two exchanges replays its own captured CUDA graph (``s7b_set_option
+  ("stage_graphs", 1)``): ~22 graph launches + 11 NCCL calls per step instead of ~170 kernel launches.
+  Capturing the whole step, NCCL included, into one graph is opt-in (``cuda_graph=True``): it deadlocked on
+  the 2-GPU boxes this was developed on;
 * layer 0 needs no exchange: ghost species are known locally, so the first-layer features of
   ghosts are recomputed (the reference's trick, ``sevenn/model_build.py:383-421``);
 * energy = one scalar all-reduce; ghost forces = one more reverse (sum) exchange of [n_ghost, 3]
@@ -30,6 +32,7 @@ between.  Here:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -294,7 +297,7 @@ class GhostExchange:
 class DistributedRunner:
     """Drives one engine per rank through the stage sequence with ghost exchanges in between
     (the protocol of ``pair_e3gnn_parallel.cpp:345-441``), overlapped as the
-    module docstring describes, and -- on CUDA with NCCL -- replayed as one captured CUDA graph."""
+    module docstring describes; on CUDA every stage between two exchanges replays its own captured CUDA graph."""
 
     def __init__(self, engine, part: Dict[str, np.ndarray], group=None, cuda_graph: Optional[bool] = None):
         import torch
@@ -316,7 +319,17 @@ class DistributedRunner:
             engine.set_interior(self.n_interior)
         self._host = None
         on_cuda = getattr(self.device, 'type', 'cpu') == 'cuda' and dist.get_backend(group) == 'nccl'
-        self.use_graph = on_cuda if cuda_graph is None else (bool(cuda_graph) and on_cuda)
+        # Launch overhead is taken out by the engine's per-stage CUDA graphs (one graph per stage between two
+        # exchanges, NCCL stays outside: option "stage_graphs").  Capturing the WHOLE step, NCCL included, into
+        # one torch.cuda.CUDAGraph is opt-in (cuda_graph=True / S7B_CUDA_GRAPH=1): on the 2-GPU boxes of this
+        # project the capture of the async all-to-all sequence deadlocked, so it is not a default.
+        if cuda_graph is None:
+            cuda_graph = os.environ.get('S7B_CUDA_GRAPH', '0') == '1'
+        self.use_graph = bool(cuda_graph) and on_cuda
+        self.stage_graphs = on_cuda and hasattr(engine, 'stage_graph_stats') and os.environ.get('S7B_STAGE_GRAPHS', '1') == '1'
+        if self.stage_graphs:
+            from .engine import set_option
+            set_option('stage_graphs', 1)
         self._graph, self._graph_key, self.graph_error = None, None, None
         self.graph_captures = self.graph_replays = 0
 
