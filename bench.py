@@ -296,7 +296,7 @@ def run_engine(args):
         part = brick_decompose(pos, cell, species_all, GRIDS[args.gpus], rank, 5.0)
         n_edges_local = part['edge_index'].shape[1]
         eng = B200Engine(meta, arrays, radial=args.radial, device=local_rank)
-        runner = DistributedRunner(eng, part)      # per-stage CUDA graphs; S7B_CUDA_GRAPH=1 opts into whole-step capture
+        runner = DistributedRunner(eng, part)      # whole step (NCCL included) as one CUDA graph; S7B_CUDA_GRAPH=0: per-stage graphs
         t = torch.tensor([n_edges_local], device=dev, dtype=torch.int64)
         dist.all_reduce(t)
         n_edges = int(t.item())
@@ -428,8 +428,11 @@ def run_engine(args):
                 'parallelism': 'single GPU' if world == 1 else f'spatial bricks {GRIDS[args.gpus]} + NCCL ghost exchange',
                 'l2': 'flushed with a 256 MiB write between timed steps',
                 'cuda_graph': (bool(int(os.environ.get('S7B_CUDA_GRAPH', '1'))) and args.radial == 'table') if world == 1
-                else ('whole step' if (runner.use_graph and runner.graph_replays > 0) else ('per stage' if runner.stage_graphs else False)),
-                'cuda_graph_note': None if world == 1 else (runner.graph_error or 'stage graphs (captures, replays) = %s; NCCL calls between the graphs' % (eng.stage_graph_stats(),)),
+                else (True if (runner.use_graph and runner.graph_replays > 0) else ('per stage' if runner.stage_graphs else False)),
+                'cuda_graph_note': None if world == 1 else (
+                    runner.graph_error or (f'{runner.graph_captures} capture(s), {runner.graph_replays} replays; NCCL calls inside the graph'
+                                           if runner.graph_replays > 0 else
+                                           'stage graphs (captures, replays) = %s; NCCL calls between the graphs' % (eng.stage_graph_stats(),))),
                 'tc_gemm': bool(int(os.environ.get('S7B_TC_GEMM', '1'))),
                 'energy_eV': float(out[0]) if world == 1 else float(out['energy'])},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
@@ -445,8 +448,26 @@ def run_engine(args):
             line['cpu_baseline'] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        shutdown(runner)
+
+
+def shutdown(runner):
+    """multi-rank teardown: the captured step graph refers to the NCCL communicator and must go first
+    (ncclCommDestroy waits for such graphs); a timer guards the teardown so that a bench line that is already
+    printed is never followed by a hung process"""
+    import threading
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    if runner is not None:
+        runner.close()
+    torch.cuda.synchronize()
+    dist.barrier()
+    guard = threading.Timer(60.0, lambda: os._exit(0))
+    guard.daemon = True
+    guard.start()
+    dist.destroy_process_group()
+    guard.cancel()
 
 
 def distributed_parity(runner, eng, meta, arrays, pos, cell, species_all, local_rank):
@@ -611,8 +632,7 @@ def run_nacl_d3(args):
                 'clocks': clocks, 'parity': parity}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        shutdown(runner)
 
 
 def roofline_from_profile(eng, prof, n_edges, n_dst):

@@ -1356,7 +1356,11 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void* stream) {
       if (sg.replays_since_capture < 2 && ++sg.thrash >= 3) return run_stage_impl(e, stage, t, stream);
     }
     if (ensure_graph_stream(e)) return 1;
-    if (capture_graph(e, [&](cudaStream_t s) { return run_stage_impl(e, stage, t, s); }, &sg.exec, &sg.launches)) return 1;
+    if (capture_graph(e, [&](cudaStream_t s) { return run_stage_impl(e, stage, t, s); }, &sg.exec, &sg.launches)) {
+      sg.exec = nullptr;                 // a stage that cannot be captured keeps its direct launches
+      sg.thrash = 3;
+      return run_stage_impl(e, stage, t, stream);
+    }
     sg.key = key;
     sg.replays_since_capture = 0;
     ++e->sg_captures;

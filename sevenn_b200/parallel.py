@@ -21,10 +21,11 @@ between.  Here:
   split at that point: the interior part of layer t runs while the ghost rows of x(t) are still in
   flight, and in the backward the boundary part runs first so that the ghost rows of dx(t) travel
   while the interior part is computed (stages 10-13 of ``include/sevenn_b200.h``);
-* on CUDA every stage between two exchanges replays its own captured CUDA graph (``s7b_set_option
-  ("stage_graphs", 1)``): ~22 graph launches + 11 NCCL calls per step instead of ~170 kernel launches.
-  Capturing the whole step, NCCL included, into one graph is opt-in (``cuda_graph=True``): it deadlocked on
-  the 2-GPU boxes this was developed on;
+* on CUDA the whole step -- kernels, pack/unpack and the NCCL calls -- is captured once into a CUDA
+  graph and replayed (``cuda_graph``), so the per-step host cost is one graph launch; ``close()`` releases
+  the graph before the process group is destroyed (NCCL waits for graphs that refer to a communicator).
+  With that turned off, every stage between two exchanges still replays its own captured graph
+  (``s7b_set_option("stage_graphs", 1)``: ~22 graph launches + 11 NCCL calls instead of ~170 kernel launches);
 * layer 0 needs no exchange: ghost species are known locally, so the first-layer features of
   ghosts are recomputed (the reference's trick, ``sevenn/model_build.py:383-421``);
 * energy = one scalar all-reduce; ghost forces = one more reverse (sum) exchange of [n_ghost, 3]
@@ -297,7 +298,7 @@ class GhostExchange:
 class DistributedRunner:
     """Drives one engine per rank through the stage sequence with ghost exchanges in between
     (the protocol of ``pair_e3gnn_parallel.cpp:345-441``), overlapped as the
-    module docstring describes; on CUDA every stage between two exchanges replays its own captured CUDA graph."""
+    module docstring describes, and -- on CUDA with NCCL -- replayed as one captured CUDA graph."""
 
     def __init__(self, engine, part: Dict[str, np.ndarray], group=None, cuda_graph: Optional[bool] = None):
         import torch
@@ -319,12 +320,13 @@ class DistributedRunner:
             engine.set_interior(self.n_interior)
         self._host = None
         on_cuda = getattr(self.device, 'type', 'cpu') == 'cuda' and dist.get_backend(group) == 'nccl'
-        # Launch overhead is taken out by the engine's per-stage CUDA graphs (one graph per stage between two
-        # exchanges, NCCL stays outside: option "stage_graphs").  Capturing the WHOLE step, NCCL included, into
-        # one torch.cuda.CUDAGraph is opt-in (cuda_graph=True / S7B_CUDA_GRAPH=1): on the 2-GPU boxes of this
-        # project the capture of the async all-to-all sequence deadlocked, so it is not a default.
+        # On CUDA the whole step -- kernels, pack/unpack and the NCCL calls -- is captured once into one
+        # torch.cuda.CUDAGraph and replayed (cuda_graph=False / S7B_CUDA_GRAPH=0 turns that off).  NCCL keeps a
+        # communicator alive while a captured graph refers to it: call close() before destroy_process_group(),
+        # otherwise the teardown waits forever.  Without the whole-step graph, every stage between two exchanges
+        # still replays its own graph (engine option "stage_graphs": NCCL stays outside the graphs).
         if cuda_graph is None:
-            cuda_graph = os.environ.get('S7B_CUDA_GRAPH', '0') == '1'
+            cuda_graph = os.environ.get('S7B_CUDA_GRAPH', '1') == '1'
         self.use_graph = bool(cuda_graph) and on_cuda
         self.stage_graphs = on_cuda and hasattr(engine, 'stage_graph_stats') and os.environ.get('S7B_STAGE_GRAPHS', '1') == '1'
         if self.stage_graphs:
@@ -437,6 +439,14 @@ class DistributedRunner:
             self.graph_error = f'{type(ex).__name__}: {ex}'[:300]
             self._graph, self.use_graph = None, False
             torch.cuda.synchronize(self.device)
+
+    def close(self):
+        """drop the captured step graph (it pins the NCCL communicator); call before destroy_process_group()"""
+        g, self._graph, self._graph_key = self._graph, None, None
+        if g is not None:
+            self.torch.cuda.synchronize(self.device)
+            g.reset()
+            self.torch.cuda.synchronize(self.device)
 
     def set_cuda_graph(self, enable: bool):
         on_cuda = getattr(self.device, 'type', 'cpu') == 'cuda' and self.dist.get_backend(self.group) == 'nccl'

@@ -29,13 +29,14 @@ def _worker(rank, world, port, grid, model, q):
     os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    run = rp = None
     try:
         meta, arrays = model_weights(model)
         pos, cell, z = diamond_si(4, 3, 3, seed=2)
         part = brick_decompose(pos, cell, species_of(meta, z), grid, rank, 5.0)
         from sevenn_b200.engine import set_option
         run = DistributedRunner(B200Engine(meta, arrays, device=rank), part)
-        assert not run.use_graph            # whole-step capture (NCCL inside the graph) is opt-in
+        run.set_cuda_graph(False)
         set_option('stage_graphs', 0)
         run.compute()                       # eager stage sequence (split convolutions, overlapped exchanges)
         torch.cuda.synchronize()
@@ -44,21 +45,20 @@ def _worker(rank, world, port, grid, model, q):
         for _ in range(3):                  # every stage between two exchanges: captured once, then replayed
             run.compute()
         torch.cuda.synchronize()
-        r = run.results()
+        r_stage = run.results()
         captures, replays = run.engine.stage_graph_stats()
         assert captures > 0 and replays == 3 * captures, (captures, replays)
+        assert abs(float(r_stage['energy'].cpu()[0]) - float(r_eager['energy'].cpu()[0])) < 1e-9
+        assert torch.allclose(r_stage['forces'], r_eager['forces'], atol=2e-6)
+        run.set_cuda_graph(True)
+        for _ in range(3):                  # capture, then replays of the whole step incl. the NCCL calls
+            run.compute()
+        torch.cuda.synchronize()
+        r = run.results()
+        assert run.graph_error is None, run.graph_error
+        assert run.graph_captures == 1 and run.graph_replays == 3
         assert abs(float(r['energy'].cpu()[0]) - float(r_eager['energy'].cpu()[0])) < 1e-9
         assert torch.allclose(r['forces'], r_eager['forces'], atol=2e-6)
-        if os.environ.get('S7B_TEST_NCCL_GRAPH') == '1':      # opt-in: the whole step incl. NCCL as one graph
-            run.set_cuda_graph(True)
-            for _ in range(3):
-                run.compute()
-            torch.cuda.synchronize()
-            rg = run.results()
-            assert run.graph_error is None, run.graph_error
-            assert run.graph_captures == 1 and run.graph_replays == 3
-            assert torch.allclose(rg['forces'], r_eager['forces'], atol=2e-6)
-            run.set_cuda_graph(False)
         h = run.compute_host()
         # positions in: partition, ghost lists and graph built on the device, send lists derived locally
         rp = DistributedRunner.from_positions(B200Engine(meta, arrays, device=rank), pos, cell, species_of(meta, z), grid)
@@ -77,6 +77,9 @@ def _worker(rank, world, port, grid, model, q):
                r['atomic_energy'].cpu().numpy(), r['virial'].cpu().numpy(), h['energy'], h['forces'].copy(),
                r3['global_ids'], r3['forces'].cpu().numpy(), float(r3['energy'].cpu()[0])))
     finally:
+        for rr in (run, rp):                # the captured graph pins the communicator: release it before the teardown
+            if rr is not None:
+                rr.close()
         dist.destroy_process_group()
 
 
@@ -98,10 +101,15 @@ def test_multi_gpu_matches_oracle(world, grid, model):
     procs = [ctx.Process(target=_worker, args=(r, world, port, grid, model, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = [q.get(timeout=300) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                     # never leave a rank behind (a hung teardown would hang pytest's exit)
+            if p.is_alive():
+                p.kill()
     forces = np.zeros((len(pos), 3))
     forces_h = np.zeros((len(pos), 3))
     forces_m = np.zeros((len(pos), 3))
@@ -157,10 +165,15 @@ def test_multi_gpu_d3_matches_single_gpu(world):
     procs = [ctx.Process(target=_d3_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = [q.get(timeout=300) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                     # never leave a rank behind (a hung teardown would hang pytest's exit)
+            if p.is_alive():
+                p.kill()
     for rank, e, f, s in res:
         assert abs(e - e1) < 1e-9 * abs(e1)
         assert np.abs(f - f1).max() < 1e-10
