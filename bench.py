@@ -459,13 +459,13 @@ def shutdown(runner):
     import torch
     import torch.distributed as dist
     sys.stdout.flush()
+    guard = threading.Timer(90.0, lambda: os._exit(0))
+    guard.daemon = True
+    guard.start()
     if runner is not None:
         runner.close()
     torch.cuda.synchronize()
     dist.barrier()
-    guard = threading.Timer(60.0, lambda: os._exit(0))
-    guard.daemon = True
-    guard.start()
     dist.destroy_process_group()
     guard.cancel()
 

@@ -322,6 +322,7 @@ static int build_layer_cfg(LayerCfg& L, const int* x_muls, int n_lx, const int* 
 
 static int g_opt_atomic_virial = 0;   // engines created afterwards also produce the per-atom virial
 static int g_opt_concurrent = 1;   // co-schedule the per-l1 convolution kernels of a layer on side streams
+static int g_opt_gate_bwd_rows = 0; // gate backward also leaves the row maxima of dg (saves one row-exponent pass per layer; opt-in)
 static int g_opt_stage_graphs = 0;  // s7b_engine_run_stage replays one captured graph per (stage, layer)
 static int g_opt_cuda_graph = 1;   // s7b_engine_compute replays a captured CUDA graph of the step (table mode)
 static int g_opt_tc_gemm = 1;   // 1 (default): node linears on tcgen05 (error-free bf16x3 slices, tc_gemm.cuh); 0: FP32 SIMT
@@ -471,7 +472,7 @@ static int launch_row_exponents(RowExp& re, const float* A, int lda, const int* 
   int rows = 0;
   for (int l = 0; l < n_l; ++l) {
     if (a_K[l] == 0) continue;
-    if (a_K[l] % 32 != 0) return fail("row exponents need K % 32 == 0");
+    if (a_K[l] % 4 != 0) return fail("row exponents need K % 4 == 0");
     const int b = r.nblocks++;
     r.d[b] = 2 * l + 1;
     r.K[b] = a_K[l];
@@ -674,6 +675,7 @@ int s7b_set_option(const char* name, int value) {
   if (std::string(name) == "concurrent_conv") { g_opt_concurrent = value; return 0; }
   if (std::string(name) == "cuda_graph") { g_opt_cuda_graph = value; return 0; }
   if (std::string(name) == "stage_graphs") { g_opt_stage_graphs = value; return 0; }
+  if (std::string(name) == "gate_bwd_rows") { g_opt_gate_bwd_rows = value; return 0; }
   return fail(std::string("unknown option: ") + name);
 }
 
@@ -1199,7 +1201,7 @@ static int run_stage_impl(S7bEngine* e, int stage, int t, void* stream) {
       if (head && t > 0 && Nn > 0) S7B_CUDA_CHECK(cudaMemsetAsync(e->dx.p, 0, (size_t)Nn * L.dim_x * sizeof(float), st));
       if (Nl == 0) return 0;
       if (head) {
-        const bool dg_rows = g_opt_tc_gemm && L.tcw.count("si2T") && L.tcw.at("si2T") && L.tcw.at("si2T")->ok && L.n_lg * L.n_lg <= 16;
+        const bool dg_rows = g_opt_gate_bwd_rows && g_opt_tc_gemm && L.tcw.count("si2T") && L.tcw.at("si2T") && L.tcw.at("si2T")->ok && L.n_lg * L.n_lg <= 16;
         {
           ProfScope ps(e->prof, st, "gate_bwd", t);
           if (dg_rows) {      // ... and the row exponents of dg for si2^T / sc^T
@@ -1301,7 +1303,7 @@ static int run_stage_impl(S7bEngine* e, int stage, int t, void* stream) {
 static std::vector<int64_t> graph_key(const S7bEngine* e) {
   return {e->n_nodes, e->n_local, e->n_interior, e->E_cap, e->n_edges > 0 ? 1 : 0, (int64_t)(uintptr_t)e->d_species,
           (int64_t)(uintptr_t)e->d_rowptr, (int64_t)(uintptr_t)e->d_src, (int64_t)(uintptr_t)e->d_edge_vec,
-          g_alloc_gen, g_opt_concurrent, g_opt_tc_gemm + 2 * g_opt_tc_swizzle, e->concurrent ? 1 : 0,
+          g_alloc_gen, g_opt_concurrent, g_opt_tc_gemm + 2 * g_opt_tc_swizzle + 4 * g_opt_gate_bwd_rows, e->concurrent ? 1 : 0,
           e->want_atomic_virial ? 1 : 0};
 }
 

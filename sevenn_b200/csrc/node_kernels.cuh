@@ -225,12 +225,11 @@ __global__ void gate_bwd_kernel(const GateDesc d, const float* __restrict__ g,
 // tensor-core linears that consume it (tc_gemm.cuh: fixed-point row scaling needs max |a| of every (l, component)
 // row): E[n, l^2 + i] = exponent with max |row| < 2^E, or zero_row for an all-zero row.  Lanes walk the node's
 // elements 32 at a time (coalesced); lanes holding elements of the same row combine with match.any + redux.sync.
-// all multiplicities are multiples of 32 (build_layer_cfg), so the 32 consecutive elements of one warp
-// iteration lie in ONE row: a single warp reduction, lane 0 keeps the running maximum
 __device__ __forceinline__ void row_max_update(unsigned int* smax, int r, float v, int lane) {
-  const unsigned int mm = __reduce_max_sync(0xffffffffu, __float_as_uint(v) & 0x7fffffffu);
-  const int rr = __shfl_sync(0xffffffffu, r, 0);
-  if (lane == 0 && rr >= 0) smax[rr] = max(smax[rr], mm);
+  const unsigned int m = __float_as_uint(v) & 0x7fffffffu;
+  const unsigned int peers = __match_any_sync(0xffffffffu, r);
+  const unsigned int mm = __reduce_max_sync(peers, m);
+  if (r >= 0 && lane == __ffs(peers) - 1) smax[r] = max(smax[r], mm);
   __syncwarp();
 }
 __device__ __forceinline__ void row_exponents_store(const unsigned int* smax, int* E, int rows, int lane, int zero_row) {

@@ -168,9 +168,9 @@ struct RowExpArgs {
 };
 
 __global__ void row_exponent_kernel(const RowExpArgs a) {
-  // one warp per node: the node's row is read once, coalesced (float4 per lane).  K is a multiple of 32, so
-  // the 8 float4 of an aligned 8-lane group lie in one (block, component) row: three shuffles reduce the group,
-  // its first lane folds the result into the row's slot in shared memory.
+  // one warp per node: the node's row is read once, coalesced (float4 per lane); every float4 lies inside one
+  // (block, component) row (K is a multiple of 4).  Lanes that hold quads of the same row combine their maxima
+  // with one warp reduction (match.any + redux.sync), its leader updates the row's slot in shared memory.
   __shared__ unsigned int smax[8][16];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -183,17 +183,18 @@ __global__ void row_exponent_kernel(const RowExpArgs a) {
       for (int q0 = 0; q0 < quads; q0 += 32) {
         const int q = q0 + lane;
         unsigned int m = 0u;
+        int r = -1;
         if (q < quads) {
           const float4 v = __ldg(row + q);
           m = __float_as_uint(v.x) & 0x7fffffffu;
           m = max(m, __float_as_uint(v.y) & 0x7fffffffu);
           m = max(m, __float_as_uint(v.z) & 0x7fffffffu);
           m = max(m, __float_as_uint(v.w) & 0x7fffffffu);
+          r = a.row_base[b] + (4 * q) / K;
         }
-        m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
-        m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        if ((lane & 7) == 0 && q < quads) atomicMax(&smax[wib][a.row_base[b] + (4 * q) / K], m);
+        const unsigned int peers = __match_any_sync(0xffffffffu, r);
+        const unsigned int mm = __reduce_max_sync(peers, m);
+        if (r >= 0 && lane == __ffs(peers) - 1) smax[wib][r] = max(smax[wib][r], mm);
         __syncwarp();
       }
     }

@@ -300,7 +300,8 @@ class DistributedRunner:
     (the protocol of ``pair_e3gnn_parallel.cpp:345-441``), overlapped as the
     module docstring describes, and -- on CUDA with NCCL -- replayed as one captured CUDA graph."""
 
-    def __init__(self, engine, part: Dict[str, np.ndarray], group=None, cuda_graph: Optional[bool] = None):
+    def __init__(self, engine, part: Dict[str, np.ndarray], group=None, cuda_graph: Optional[bool] = None,
+                 stage_graphs: Optional[bool] = None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group = torch, dist, group
@@ -328,11 +329,14 @@ class DistributedRunner:
         if cuda_graph is None:
             cuda_graph = os.environ.get('S7B_CUDA_GRAPH', '1') == '1'
         self.use_graph = bool(cuda_graph) and on_cuda
-        self.stage_graphs = on_cuda and hasattr(engine, 'stage_graph_stats') and os.environ.get('S7B_STAGE_GRAPHS', '1') == '1'
-        if self.stage_graphs:
+        if stage_graphs is None:            # the fallback when the whole-step graph is off and the graph arrays are static
+            stage_graphs = not self.use_graph and 'send_lists' not in part and os.environ.get('S7B_STAGE_GRAPHS', '1') == '1'
+        self.stage_graphs = bool(stage_graphs) and on_cuda and hasattr(engine, 'stage_graph_stats')
+        if on_cuda and hasattr(engine, 'stage_graph_stats'):
             from .engine import set_option
-            set_option('stage_graphs', 1)
+            set_option('stage_graphs', 1 if self.stage_graphs else 0)
         self._graph, self._graph_key, self.graph_error = None, None, None
+        self._graph_ptrs = None             # device addresses of the graph arrays the engine currently reads
         self.graph_captures = self.graph_replays = 0
 
     def _buf(self, name, t, width):
@@ -360,6 +364,7 @@ class DistributedRunner:
         if self.split:
             self.engine.set_interior(self.n_interior)
         self._graph, self._host = None, None
+        self._graph_ptrs = tuple(part[k].data_ptr() for k in ('species', 'rowptr', 'src', 'edge_vec'))
         return self
 
     def _all_reduce_f8(self, name):
@@ -417,7 +422,7 @@ class DistributedRunner:
     def _key(self):
         eng = self.engine
         return (self.n_nodes, self.n_local, int(eng.n_edges), eng.buffer('forces', shape=(self.n_nodes, 3)).data_ptr(),
-                self._buf('x', self.n_layers - 1, eng.spec.layers[-1].dim_x).data_ptr())
+                self._buf('x', self.n_layers - 1, eng.spec.layers[-1].dim_x).data_ptr(), self._graph_ptrs)
 
     def _capture(self):
         """capture the step (kernels + NCCL) into a CUDA graph; any failure falls back to eager stages"""
@@ -504,6 +509,8 @@ class DistributedRunner:
         for k in ('species', 'rowptr', 'src', 'vec'):
             d[k].copy_(h[k], non_blocking=True)
         self.engine.set_graph_csr(d['species'], d['rowptr'], d['src'], d['vec'], self.n_local)
+        # a captured step bakes these addresses in: the first host-entry step re-captures against the staging arrays
+        self._graph_ptrs = tuple(d[k].data_ptr() for k in ('species', 'rowptr', 'src', 'vec'))
         if self.split:
             self.engine.set_interior(self.n_interior)
         self.compute()

@@ -107,69 +107,3 @@ def test_nve_md_conserves_energy(engine):
     captures, replays = engine.graph_stats()
     assert replays == 201 and captures <= 3, (captures, replays)
 
-
-def _split_sequence(eng, T):
-    """the runner's stage order with the interior / boundary split, exchanges left out (single GPU)"""
-    from sevenn_b200 import engine as E
-    eng.run_stage(E.STAGE_FWD_BEGIN)
-    for t in range(T):
-        if t == 0:
-            eng.run_stage(E.STAGE_FWD_LAYER_A, t)
-        else:
-            eng.run_stage(E.STAGE_FWD_CONV_INTERIOR, t)
-            eng.run_stage(E.STAGE_FWD_LAYER_A2, t)
-        eng.run_stage(E.STAGE_FWD_LAYER_SC, t)
-    eng.run_stage(E.STAGE_FWD_END)
-    for t in range(T - 1, -1, -1):
-        if t == 0:
-            eng.run_stage(E.STAGE_BWD_LAYER_A, t)
-            continue
-        eng.run_stage(E.STAGE_BWD_LAYER_A1, t)
-        eng.run_stage(E.STAGE_BWD_LAYER_A2, t)
-        eng.run_stage(E.STAGE_BWD_LAYER_B1, t)
-        eng.run_stage(E.STAGE_BWD_LAYER_B2, t)
-    eng.run_stage(E.STAGE_BWD_END)
-
-
-def test_stage_graphs_equal_direct_stage_launches(engine):
-    """option stage_graphs: one captured graph per (stage, layer), replayed on the caller's stream; a changed
-    graph key (set_interior) re-captures; an entry whose key never settles falls back to direct launches"""
-    import torch
-    from sevenn_b200.engine import set_option
-    pos, cell = _si((3, 2, 2))
-    sp = np.full(len(pos), engine.spec.type_map[14], dtype=np.int32)
-    engine.set_positions(sp, pos, cell, True)
-    T = engine.spec.n_layers
-    engine.compute(); torch.cuda.synchronize()
-    ref = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
-    try:
-        engine.set_interior(len(pos) // 3)
-        set_option('stage_graphs', 0)
-        _split_sequence(engine, T); torch.cuda.synchronize()
-        direct = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
-        assert engine.stage_graph_stats() == (0, 0)
-        set_option('stage_graphs', 1)
-        for _ in range(3):
-            _split_sequence(engine, T)
-        torch.cuda.synchronize()
-        out = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
-        captures, replays = engine.stage_graph_stats()
-        assert captures == 5 + T + 6 * (T - 1) and replays == 3 * captures      # one per run_stage call of the sequence
-        for res in (direct, out):
-            assert abs(res['energy'][0] - ref['energy'][0]) < 1e-6
-            assert np.allclose(res['forces'], ref['forces'], atol=2e-6)
-            assert np.allclose(res['virial'], ref['virial'], atol=1e-5)
-        engine.set_interior(len(pos) // 2)          # another split point: every stage re-captures once
-        _split_sequence(engine, T); _split_sequence(engine, T); torch.cuda.synchronize()
-        out2 = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
-        assert engine.stage_graph_stats()[0] == 2 * captures
-        assert np.allclose(out2['forces'], ref['forces'], atol=2e-6)
-        for i in range(5):                          # the key changes on every step: capturing stops after three tries
-            engine.set_interior(10 + i)
-            _split_sequence(engine, T)
-        torch.cuda.synchronize()
-        out3 = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
-        assert engine.stage_graph_stats()[0] <= 2 * captures + 3 * captures
-        assert np.allclose(out3['forces'], ref['forces'], atol=2e-6)
-    finally:
-        set_option('stage_graphs', 0)

@@ -1,0 +1,117 @@
+"""Opt-in engine features that the default path does not use (file name sorts last on purpose: these were written
+after the round's last GPU session and a failure here must not hide the default-path suites under ``-x``):
+per-stage CUDA graphs (option ``stage_graphs``) and the gate backward that also leaves the row maxima of dg
+(option ``gate_bwd_rows``)."""
+import numpy as np
+import pytest
+
+from helpers import model_weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def engine():
+    from sevenn_b200.engine import B200Engine, set_option
+    meta, arrays = model_weights('sevennet_0')
+    yield B200Engine(meta, arrays)
+    set_option('stage_graphs', 0)
+    set_option('gate_bwd_rows', 0)
+
+
+def _si(reps, seed=0, sigma=0.05, a=5.431):
+    from sevenn_b200.neighbors import diamond_si
+    pos, cell, _ = diamond_si(*reps, a=a, sigma=sigma, seed=seed)
+    return pos, cell
+
+
+def _split_sequence(eng, T):
+    """the runner's stage order with the interior / boundary split, exchanges left out (single GPU)"""
+    from sevenn_b200 import engine as E
+    eng.run_stage(E.STAGE_FWD_BEGIN)
+    for t in range(T):
+        if t == 0:
+            eng.run_stage(E.STAGE_FWD_LAYER_A, t)
+        else:
+            eng.run_stage(E.STAGE_FWD_CONV_INTERIOR, t)
+            eng.run_stage(E.STAGE_FWD_LAYER_A2, t)
+        eng.run_stage(E.STAGE_FWD_LAYER_SC, t)
+    eng.run_stage(E.STAGE_FWD_END)
+    for t in range(T - 1, -1, -1):
+        if t == 0:
+            eng.run_stage(E.STAGE_BWD_LAYER_A, t)
+            continue
+        eng.run_stage(E.STAGE_BWD_LAYER_A1, t)
+        eng.run_stage(E.STAGE_BWD_LAYER_A2, t)
+        eng.run_stage(E.STAGE_BWD_LAYER_B1, t)
+        eng.run_stage(E.STAGE_BWD_LAYER_B2, t)
+    eng.run_stage(E.STAGE_BWD_END)
+
+
+def test_stage_graphs_equal_direct_stage_launches(engine):
+    """option stage_graphs: one captured graph per (stage, layer), replayed on the caller's stream; a changed
+    graph key (set_interior) re-captures; an entry whose key never settles falls back to direct launches"""
+    import torch
+    from sevenn_b200.engine import set_option
+    pos, cell = _si((3, 2, 2))
+    sp = np.full(len(pos), engine.spec.type_map[14], dtype=np.int32)
+    engine.set_positions(sp, pos, cell, True)
+    T = engine.spec.n_layers
+    engine.compute(); torch.cuda.synchronize()
+    ref = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
+    try:
+        engine.set_interior(len(pos) // 3)
+        set_option('stage_graphs', 0)
+        _split_sequence(engine, T); torch.cuda.synchronize()
+        direct = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
+        assert engine.stage_graph_stats() == (0, 0)
+        set_option('stage_graphs', 1)
+        for _ in range(3):
+            _split_sequence(engine, T)
+        torch.cuda.synchronize()
+        out = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
+        captures, replays = engine.stage_graph_stats()
+        assert captures == 5 + T + 6 * (T - 1) and replays == 3 * captures      # one per run_stage call of the sequence
+        for res in (direct, out):
+            assert abs(res['energy'][0] - ref['energy'][0]) < 1e-6
+            assert np.allclose(res['forces'], ref['forces'], atol=2e-6)
+            assert np.allclose(res['virial'], ref['virial'], atol=1e-5)
+        engine.set_interior(len(pos) // 2)          # another split point: every stage re-captures once
+        _split_sequence(engine, T); _split_sequence(engine, T); torch.cuda.synchronize()
+        out2 = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
+        assert engine.stage_graph_stats()[0] == 2 * captures
+        assert np.allclose(out2['forces'], ref['forces'], atol=2e-6)
+        for i in range(5):                          # the key changes on every step: capturing stops after three tries
+            engine.set_interior(10 + i)
+            _split_sequence(engine, T)
+        torch.cuda.synchronize()
+        out3 = {k: v.cpu().numpy().copy() for k, v in engine.results().items()}
+        assert engine.stage_graph_stats()[0] <= 2 * captures + 3 * captures
+        assert np.allclose(out3['forces'], ref['forces'], atol=2e-6)
+    finally:
+        set_option('stage_graphs', 0)
+
+
+@pytest.mark.parametrize('model', ['sevennet_0', 'sevennet_l3i5'])
+def test_gate_bwd_rows_option_matches_default(model):
+    """option gate_bwd_rows: same forces as the default (separate row-exponent pass over dg) -- the row maxima
+    are the same numbers, so the tensor-core slices and every result must be bit-identical up to RED.ADD order"""
+    import torch
+    from sevenn_b200.engine import B200Engine, set_option
+    meta, arrays = model_weights(model)
+    eng = B200Engine(meta, arrays)
+    pos, cell = _si((2, 2, 3), seed=4)
+    sp = np.full(len(pos), eng.spec.type_map[14], dtype=np.int32)
+    try:
+        set_option('gate_bwd_rows', 0)
+        eng.set_positions(sp, pos, cell, True)
+        eng.compute(); torch.cuda.synchronize()
+        ref = {k: v.cpu().numpy().copy() for k, v in eng.results().items()}
+        set_option('gate_bwd_rows', 1)
+        eng.compute(); torch.cuda.synchronize()
+        out = {k: v.cpu().numpy().copy() for k, v in eng.results().items()}
+    finally:
+        set_option('gate_bwd_rows', 0)
+    assert out['energy'][0] == ref['energy'][0]
+    assert np.allclose(out['forces'], ref['forces'], atol=2e-6)
+    assert np.allclose(out['virial'], ref['virial'], atol=1e-5)
