@@ -530,7 +530,7 @@ def run_nacl_d3(args):
     meta, arrays = load_weights(os.path.join(ROOT, 'weights', 'sevennet_0.npz'))
     tm = {int(k): int(v) for k, v in meta['type_map'].items()}
     cells = (25, 25, 10) if args.cells is None else tuple(args.cells)
-    pos, cell, z = rocksalt_nacl(*cells, sigma=0.05, seed=0)
+    pos, cell, z = rocksalt_nacl(*cells, a=args.nacl_a, sigma=0.05, seed=0)
     n_atoms = len(z)
     species = np.array([tm[int(a)] for a in z], dtype=np.int32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -622,7 +622,7 @@ def run_nacl_d3(args):
         line = {'metric': METRIC, 'value': n_atoms / (ms * 1e-3), 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
                 'vs_baseline': None, 'dtype': 'f32 (network), f32 pair terms / f64 sums (D3)', 'data': 'synthetic',
-                'config': {'workload': f'SevenNet-0 + D3(BJ, pbe, 9000/1600 bohr^2) energy+forces per MD step, rocksalt NaCl '
+                'config': {'workload': f'SevenNet-0 + D3(BJ, pbe, 9000/1600 bohr^2) energy+forces per MD step, rocksalt NaCl a = {args.nacl_a} A, '
                                        f'{cells[0]}x{cells[1]}x{cells[2]} cells = {n_atoms} atoms, {n_edges} network edges',
                            'parallelism': 'single GPU' if world == 1 else f'network: spatial bricks {GRIDS[args.gpus]} + NCCL ghost exchange; '
                                           f'D3: atom decomposition, replicated positions, 3 all-gathers',
@@ -734,6 +734,8 @@ def main():
     ap.add_argument('--no-extras', action='store_true', help='skip the l3i5 / gpu_standin legs of the N = 1 line')
     ap.add_argument('--workload', default='si', choices=['si', 'nacl_d3'],
                     help="'si': the headline benchmark (BASELINE configs[1]/[3]); 'nacl_d3': configs[4], SevenNet-0 + D3 on NaCl")
+    ap.add_argument('--nacl-a', type=float, default=5.64,
+                    help='lattice constant of the nacl_d3 workload; 4.0 is the dense variant of SURVEY 8(d).5 (about 65 neighbours per atom)')
     args = ap.parse_args()
     if args.gpus not in CELLS:
         raise SystemExit('--gpus must be 1, 2, 4 or 8')
