@@ -176,6 +176,21 @@ S7B_API int s7b_engine_compute_host(S7bEngine* eng, int32_t n_nodes, int64_t n_e
                             const int32_t* edge_neighbour, const float* edge_vec, double* energy,
                             float* atomic_energy, float* forces, double* virial, void* stream);
 
+/* Host-staged stage protocol (a LAMMPS pair style that exchanges ghost rows through MPI host buffers, as
+ * PairE3GNNParallel does without CUDA-aware MPI, pair_e3gnn_parallel.cpp:698-799): the graph with ghosts from host
+ * arrays (edges as (centre, neighbour, vector) sorted by centre, centres < n_local, neighbours < n_nodes), and
+ * rows [row_begin, row_begin + n_rows) of an fp32 engine buffer (names of s7b_engine_buffer; `width` floats per
+ * row) copied to / from the host between the stages.  All three synchronise the stream. */
+S7B_API int s7b_engine_set_graph_host(S7bEngine* eng, int32_t n_nodes, int32_t n_local, int64_t n_edges,
+                                      const int32_t* species, const int32_t* edge_centre, const int32_t* edge_neighbour,
+                                      const float* edge_vec, void* stream);
+S7B_API int s7b_engine_read_rows_host(S7bEngine* eng, const char* name, int layer, int32_t row_begin, int32_t n_rows,
+                                      int32_t width, float* host_out, void* stream);
+S7B_API int s7b_engine_write_rows_host(S7bEngine* eng, const char* name, int layer, int32_t row_begin, int32_t n_rows,
+                                       int32_t width, const float* host_in, void* stream);
+/* energy (1 double) and virial (6 doubles: xx,yy,zz,xy,yz,zx of -sum r (x) f) of the last BWD_END; either may be NULL */
+S7B_API int s7b_engine_read_scalars_host(S7bEngine* eng, double* energy, double* virial6, void* stream);
+
 /* Positions in: builds the neighbour list / CSR graph on the device (cell list over the
  * fractional cell, any cell size and shape, per-direction pbc) with the semantics of the reference's
  * graph builder (sevenn/train/dataload.py:32-129: every image pair with |r_j - r_i + S.cell| < cutoff,

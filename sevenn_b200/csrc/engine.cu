@@ -1663,6 +1663,84 @@ static int build_neighbor_list(S7bEngine* e, int32_t n_atoms, const int32_t* spe
   return 0;
 }
 
+// ---- host-staged pieces of the stage protocol (a LAMMPS pair style without CUDA headers: pair_e3gnn_parallel.cpp
+// does the same staging through CPU tensors unless MPI is CUDA-aware, :698-799) -----------------------------------
+// Graph with ghosts from host arrays: the upload of s7b_engine_compute_host, but n_local <= n_nodes and no compute.
+int s7b_engine_set_graph_host(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t n_edges, const int32_t* species,
+                              const int32_t* edge_centre, const int32_t* edge_neighbour, const float* edge_vec,
+                              void* stream) {
+  if (!e) return fail("null engine");
+  if (n_nodes < 0 || n_local < 0 || n_local > n_nodes || n_edges < 0) return fail("bad sizes");
+  if (n_nodes > 0 && !species) return fail("null species");
+  if (n_edges > 0 && (!edge_centre || !edge_neighbour || !edge_vec)) return fail("null edge arrays");
+  for (int64_t k = 0; k < n_edges; ++k)
+    if (edge_centre[k] < 0 || edge_centre[k] >= n_local) return fail("edge centres must be owned atoms (< n_local)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t E = (size_t)std::max<int64_t>(n_edges, 1), N = (size_t)std::max(n_nodes, 1);
+  if (e->hs_species.ensure(N * sizeof(int)) || e->hs_rowptr.ensure((N + 1) * sizeof(int)) ||
+      e->hs_src.ensure(E * sizeof(int)) || e->hs_vec.ensure(E * 3 * sizeof(float)) ||
+      e->hs_centre.ensure(E * sizeof(int)) || e->hs_flag.ensure(sizeof(int)))
+    return fail("cudaMalloc failed for staging buffers");
+  if (n_nodes > 0) S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_species.p, species, (size_t)n_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+  S7B_CUDA_CHECK(cudaMemsetAsync(e->hs_flag.p, 0, sizeof(int), st));
+  if (n_edges > 0) {
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_centre.p, edge_centre, (size_t)n_edges * sizeof(int), cudaMemcpyHostToDevice, st));
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_src.p, edge_neighbour, (size_t)n_edges * sizeof(int), cudaMemcpyHostToDevice, st));
+    S7B_CUDA_CHECK(cudaMemcpyAsync(e->hs_vec.p, edge_vec, (size_t)n_edges * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  // CSR over all n_nodes rows (ghost rows are empty, so its first n_local + 1 entries are the CSR over the owned atoms)
+  const int64_t nthreads = n_edges + 1;
+  csr_from_sorted_kernel<<<(int)((nthreads + 255) / 256), 256, 0, st>>>(e->hs_centre.as<int>(), e->hs_src.as<int>(), n_edges, n_nodes, e->hs_rowptr.as<int>(), e->hs_flag.as<int>());
+  S7B_LAUNCH_CHECK();
+  int flag = 0;
+  S7B_CUDA_CHECK(cudaMemcpyAsync(&flag, e->hs_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  S7B_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (flag & 1) return fail("edges must be sorted by centre");
+  if (flag & 2) return fail("edge neighbour index out of range");
+  return s7b_engine_set_graph(e, n_nodes, n_local, n_edges, e->hs_species.as<int>(), e->hs_rowptr.as<int>(), e->hs_src.as<int>(), e->hs_vec.as<float>(), stream);
+}
+
+// rows [row_begin, row_begin + n_rows) of a 2-D engine buffer <-> host (fp32 buffers only; synchronous)
+static int rows_host_copy(S7bEngine* e, const char* name, int layer, int32_t row_begin, int32_t n_rows, int32_t width,
+                          float* host, bool to_host, void* stream) {
+  if (!e) return fail("null engine");
+  if (n_rows <= 0) return 0;
+  if (!host || width <= 0 || row_begin < 0) return fail("bad row range");
+  const std::string nm(name ? name : "");
+  if (nm == "energy" || nm == "virial") return fail("energy / virial are doubles: read them with s7b_engine_buffer");
+  size_t numel = 0;
+  float* base = static_cast<float*>(s7b_engine_buffer(e, name, layer, &numel));
+  if (!base) return fail(std::string("no such buffer: ") + nm);
+  if ((size_t)(row_begin + (int64_t)n_rows) * width > numel) return fail("row range exceeds the buffer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* dev = base + (size_t)row_begin * width;
+  const size_t bytes = (size_t)n_rows * width * sizeof(float);
+  if (to_host) S7B_CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+  else S7B_CUDA_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st));
+  S7B_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int s7b_engine_read_rows_host(S7bEngine* e, const char* name, int layer, int32_t row_begin, int32_t n_rows, int32_t width,
+                              float* host_out, void* stream) {
+  return rows_host_copy(e, name, layer, row_begin, n_rows, width, host_out, true, stream);
+}
+
+int s7b_engine_write_rows_host(S7bEngine* e, const char* name, int layer, int32_t row_begin, int32_t n_rows, int32_t width,
+                               const float* host_in, void* stream) {
+  return rows_host_copy(e, name, layer, row_begin, n_rows, width, const_cast<float*>(host_in), false, stream);
+}
+
+int s7b_engine_read_scalars_host(S7bEngine* e, double* energy, double* virial6, void* stream) {
+  if (!e) return fail("null engine");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (energy) S7B_CUDA_CHECK(cudaMemcpyAsync(energy, e->energy.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (virial6) S7B_CUDA_CHECK(cudaMemcpyAsync(virial6, e->virial.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  S7B_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+
 int s7b_engine_set_positions_host(S7bEngine* e, int32_t n_atoms, const int32_t* species, const double* positions,
                                   const double* cell9, const int32_t* pbc3, void* stream) {
   int64_t n_edges = 0;

@@ -55,7 +55,8 @@ EXPORTS = [
     'pair_run_settings', 'pair_run_coeff', 'pair_run_compute', 'pair_get_energy', 'pair_get_force', 'pair_get_stress', 'pair_fin',
     's7b_engine_set_param', 's7b_engine_set_graph', 's7b_engine_run_stage', 's7b_engine_compute',
     's7b_engine_buffer', 's7b_engine_compute_host', 's7b_engine_set_positions_host',
-    's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_graph_stats', 's7b_engine_stage_graph_stats', 's7b_engine_set_profiling',
+    's7b_engine_compute_positions_host', 's7b_launch_count', 's7b_engine_graph_stats', 's7b_engine_stage_graph_stats', 's7b_engine_set_graph_host',
+    's7b_engine_read_rows_host', 's7b_engine_write_rows_host', 's7b_engine_read_scalars_host', 's7b_engine_set_profiling',
     's7b_engine_profile_count', 's7b_engine_profile_entry', 's7b_conv_plan_create',
     's7b_conv_plan_destroy', 's7b_conv_plan_dims', 's7b_conv_forward', 's7b_conv_backward',
 ]
@@ -115,6 +116,10 @@ def load_library() -> ctypes.CDLL:
     lib.s7b_launch_count.restype = i64
     lib.s7b_engine_graph_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.s7b_engine_stage_graph_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.s7b_engine_set_graph_host.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp]
+    lib.s7b_engine_read_rows_host.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, i32, i32, i32, vp, vp]
+    lib.s7b_engine_write_rows_host.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, i32, i32, i32, vp, vp]
+    lib.s7b_engine_read_scalars_host.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), vp]
     lib.s7b_conv_plan_create.argtypes = [i32, ctypes.POINTER(i32), i32, i32, ctypes.POINTER(vp)]
     lib.s7b_conv_plan_destroy.argtypes = [vp]
     lib.s7b_conv_plan_destroy.restype = None
@@ -372,6 +377,40 @@ class B200Engine:
             check(self.lib.s7b_engine_set_graph(
                 self._h, self.n_nodes, self.n_local, self.n_edges, species.data_ptr(),
                 rowptr.data_ptr(), src.data_ptr(), edge_vec.data_ptr(), self._stream()))
+
+    # ---- host-staged stage protocol (what examples/lammps/pair_e3gnn_b200_parallel.cpp calls) -----------------
+    def set_graph_host(self, species, edge_centre, edge_neighbour, edge_vec, n_local: int):
+        """graph with ghosts from host arrays: edges sorted by centre, centres < n_local (``s7b_engine_set_graph_host``)"""
+        sp = np.ascontiguousarray(species, dtype=np.int32)
+        c = np.ascontiguousarray(edge_centre, dtype=np.int32)
+        nb = np.ascontiguousarray(edge_neighbour, dtype=np.int32)
+        v = np.ascontiguousarray(edge_vec, dtype=np.float32)
+        with self.torch.cuda.device(self.device):
+            check(self.lib.s7b_engine_set_graph_host(self._h, len(sp), int(n_local), len(c), sp.ctypes.data, c.ctypes.data,
+                                                     nb.ctypes.data, v.ctypes.data, self._stream()))
+        self._graph = dict(perm=None)
+        self.n_nodes, self.n_local, self.n_edges = len(sp), int(n_local), len(c)
+        return self
+
+    def read_rows(self, name: str, layer: int, row_begin: int, n_rows: int, width: int) -> np.ndarray:
+        out = np.empty((n_rows, width), dtype=np.float32)
+        with self.torch.cuda.device(self.device):
+            check(self.lib.s7b_engine_read_rows_host(self._h, name.encode(), int(layer), int(row_begin), int(n_rows), int(width),
+                                                     out.ctypes.data, self._stream()))
+        return out
+
+    def write_rows(self, name: str, layer: int, row_begin: int, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        with self.torch.cuda.device(self.device):
+            check(self.lib.s7b_engine_write_rows_host(self._h, name.encode(), int(layer), int(row_begin), rows.shape[0],
+                                                      rows.shape[1], rows.ctypes.data, self._stream()))
+
+    def read_scalars(self):
+        """(energy, virial[6]) of the last BWD_END as host doubles"""
+        e, v = ctypes.c_double(), (ctypes.c_double * 6)()
+        with self.torch.cuda.device(self.device):
+            check(self.lib.s7b_engine_read_scalars_host(self._h, ctypes.byref(e), v, self._stream()))
+        return float(e.value), np.array(list(v))
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)

@@ -33,6 +33,11 @@ struct NeighList {
 };
 namespace NeighConst { enum { REQ_DEFAULT = 0, REQ_FULL = 1 }; }
 struct Neighbor { void *add_request(class Pair *, int); };
+struct Comm {
+  int me, nprocs;
+  void forward_comm(class Pair *, int size = 0);
+  void reverse_comm(class Pair *, int size = 0);
+};
 class Pointers {
  public:
   explicit Pointers(LAMMPS *) {}
@@ -43,6 +48,7 @@ class Pointers {
   Atom *atom;
   Force *force;
   Neighbor *neighbor;
+  Comm *comm;
 };
 class Pair : protected Pointers {
  public:
@@ -52,6 +58,11 @@ class Pair : protected Pointers {
   virtual void coeff(int, char **) = 0;
   virtual void init_style() {}
   virtual double init_one(int, int) { return 0.0; }
+  virtual int pack_forward_comm(int, int *, double *, int, int *) { return 0; }
+  virtual void unpack_forward_comm(int, int, double *) {}
+  virtual int pack_reverse_comm(int, int, double *) { return 0; }
+  virtual void unpack_reverse_comm(int, int *, double *) {}
+  int comm_forward = 0, comm_reverse = 0;
   double eng_vdwl, virial[6];
   double *eatom, **vatom;
  protected:

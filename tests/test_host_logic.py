@@ -140,3 +140,5 @@ def test_cpp_examples_compile(tmp_path):
                     str(tmp_path / 'host_entry'), f'-L{lib_dir}', '-lsevenn_b200', f'-Wl,-rpath,{lib_dir}'], check=True)
     subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-Werror', '-I', os.path.join(root, 'tests', 'mock_lammps'),
                     os.path.join(root, 'examples', 'lammps', 'pair_e3gnn_b200.cpp')], check=True)
+    subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-Werror', '-I', os.path.join(root, 'tests', 'mock_lammps'),
+                    os.path.join(root, 'examples', 'lammps', 'pair_e3gnn_b200_parallel.cpp')], check=True)

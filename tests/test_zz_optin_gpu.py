@@ -115,3 +115,83 @@ def test_gate_bwd_rows_option_matches_default(model):
     assert out['energy'][0] == ref['energy'][0]
     assert np.allclose(out['forces'], ref['forces'], atol=2e-6)
     assert np.allclose(out['virial'], ref['virial'], atol=1e-5)
+
+
+@pytest.mark.parametrize('model', ['sevennet_0'])
+def test_host_staged_stage_protocol_two_ranks_on_one_gpu(model):
+    """The protocol of examples/lammps/pair_e3gnn_b200_parallel.cpp through the same C entry points
+    (s7b_engine_set_graph_host / read_rows_host / write_rows_host / read_scalars_host): two bricks of one cell,
+    one engine each on the same GPU, ghost rows exchanged through host arrays between the stages.  Must reproduce
+    the single-engine evaluation of the whole cell."""
+    import torch
+    from sevenn_b200 import engine as E
+    from sevenn_b200.engine import B200Engine
+    from sevenn_b200.neighbors import build_graph, diamond_si
+    from sevenn_b200.parallel import brick_decompose
+    from helpers import species_of
+    meta, arrays = model_weights(model)
+    pos, cell, z = diamond_si(4, 2, 2, seed=3)
+    sp_all = species_of(meta, z)
+    ei, ev = build_graph(pos, cell, True, 5.0)
+    whole = B200Engine(meta, arrays)
+    whole.set_graph(sp_all, ei, ev)
+    whole.compute(); torch.cuda.synchronize()
+    ref = {k: v.cpu().numpy().copy() for k, v in whole.results().items()}
+
+    world = 2
+    parts = [brick_decompose(pos, cell, sp_all, (2, 1, 1), r, 5.0) for r in range(world)]
+    engs = [B200Engine(meta, arrays) for _ in range(world)]
+    owner_row = {}                                   # global id -> (rank, owned row)
+    for r, p in enumerate(parts):
+        order = np.argsort(p['edge_index'][0], kind='stable')
+        engs[r].set_graph_host(p['species'], p['edge_index'][0][order], p['edge_index'][1][order], p['edge_vec'][order], p['n_local'])
+        for row, g in enumerate(p['global_ids'][:p['n_local']]):
+            owner_row[int(g)] = (r, row)
+    T = engs[0].spec.n_layers
+
+    def forward(name, layer, width):                 # ghost rows <- owners' rows
+        owned = [engs[r].read_rows(name, layer, 0, parts[r]['n_local'], width) for r in range(world)]
+        for r, p in enumerate(parts):
+            ghosts = p['global_ids'][p['n_local']:]
+            if len(ghosts):
+                rows = np.stack([owned[owner_row[int(g)][0]][owner_row[int(g)][1]] for g in ghosts])
+                engs[r].write_rows(name, layer, p['n_local'], rows)
+
+    def reverse(name, layer, width):                 # owners' rows += the ghost rows that stand for them
+        full = [engs[r].read_rows(name, layer, 0, parts[r]['n_nodes'], width) for r in range(world)]
+        acc = [full[r][:parts[r]['n_local']].astype(np.float64) for r in range(world)]
+        for r, p in enumerate(parts):
+            for k, g in enumerate(p['global_ids'][p['n_local']:]):
+                q, row = owner_row[int(g)]
+                acc[q][row] += full[r][p['n_local'] + k]
+        for r in range(world):
+            engs[r].write_rows(name, layer, 0, acc[r].astype(np.float32))
+        return acc
+
+    for e in engs:
+        e.run_stage(E.STAGE_FWD_BEGIN)
+    for t in range(T):
+        for e in engs:
+            e.run_stage(E.STAGE_FWD_LAYER, t)
+        if t + 1 < T:
+            forward('x', t + 1, engs[0].spec.layers[t + 1].dim_x)
+    for e in engs:
+        e.run_stage(E.STAGE_FWD_END)
+    for t in range(T - 1, -1, -1):
+        for e in engs:
+            e.run_stage(E.STAGE_BWD_LAYER_A, t)
+        if t > 0:
+            reverse('dx', t, engs[0].spec.layers[t].dim_x)
+            for e in engs:
+                e.run_stage(E.STAGE_BWD_LAYER_B, t)
+    for e in engs:
+        e.run_stage(E.STAGE_BWD_END)
+    forces = reverse('forces', 0, 3)
+    energy = sum(e.read_scalars()[0] for e in engs)
+    virial = sum(e.read_scalars()[1] for e in engs)
+    f_all = np.zeros((len(pos), 3))
+    for r, p in enumerate(parts):
+        f_all[p['global_ids'][:p['n_local']]] = forces[r]
+    assert abs(energy - ref['energy'][0]) < 2e-5
+    assert np.allclose(f_all, ref['forces'], atol=5e-6)
+    assert np.allclose(virial, ref['virial'], atol=5e-4)
