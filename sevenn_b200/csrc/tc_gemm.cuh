@@ -16,19 +16,19 @@
 // (the dropped A1*B2, A2*B1, A2*B2 are < 2^-24 relative).  Six kind::f16 (bf16) MMAs per K = 16 step cost
 // the same tensor time as 3xTF32.  Emulated bit for bit on the CPU by tests/test_tc_pack_cpu.py.
 //
-// Structure (persistent, one CTA per SM, 352 threads, tiles of 128 rows x NT <= 128 columns):
-//   warp 8   TMA producer A: per 32-wide K chunk one cp.async.bulk.tensor (3-D map over (k, component,
+// Structure (persistent, one CTA per SM, 480 threads = 15 warps, tiles of 128 rows x NT <= 128 columns):
+//   warp 12  TMA producer A: per 32-wide K chunk one cp.async.bulk.tensor (3-D map over (k, component,
 //            node); 128B swizzle) for the raw fp32 A tile into a 5-deep ring (the HBM/L2 round trip of
-//            these loads is what bounds the kernel: 80 KB in flight per SM)
-//   warp 10  TMA producer W: one cp.async.bulk per chunk for the pre-sliced, pre-arranged W chunk (3-deep ring)
-//   warps 0-3 transform: thread r pulls row r of a raw chunk into registers (freeing its slot), converts it
-//            into the three bf16 slices and writes them in the canonical K-major UMMA layout (8-row x
-//            16-byte core matrices) into a 2-deep operand ring
-//   warp 9   MMA issuer: one thread issues 12 tcgen05.mma per chunk (M = 128, N = NT, K = 16) into the
-//            two TMEM accumulators of the tile; tcgen05.commit frees the operand slots / publishes the tile
-//   warps 4-7 epilogue: tcgen05.ld the accumulators (double-buffered in TMEM, so the next tile's MMAs
-//            overlap), scale, transpose a 32x32 slab through shared memory and write/accumulate C with
-//            128-byte coalesced row segments.
+//            these loads is what has to be hidden: 80 KB in flight per SM)
+//   warp 14  producer W: one cp.async.bulk per chunk for the pre-sliced, pre-arranged W chunk (3-deep ring)
+//   warps 0-7 transform: two threads per row of a raw chunk (16 of its 32 k each) pull it into registers
+//            (freeing the raw slot), cut it into the three bf16 slices with packed fp32x2 arithmetic and write
+//            them in the canonical K-major UMMA layout (8-row x 16-byte core matrices) into a 2-deep operand ring
+//   warp 13  TMEM allocation + MMA issuer: one thread issues 12 tcgen05.mma per chunk (M = 128, N = NT, K = 16)
+//            into the two TMEM accumulators of the tile; tcgen05.commit frees the operand slots / publishes the tile
+//   warps 8-11 epilogue: tcgen05.ld the accumulators (double-buffered in TMEM, so the next tile's MMAs
+//            overlap), scale, transpose a 32x32 slab through shared memory (STS.128 / LDS.128) and write C with
+//            128-bit row segments, or RED.ADD.F32x4 when accumulating.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
