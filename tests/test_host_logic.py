@@ -67,6 +67,48 @@ def test_neighbor_small_cell_counts_images():
     assert (np.linalg.norm(ev, axis=1) < 5.0).all()
 
 
+def test_neighbor_counts_held_by_the_reference_tests():
+    """tests/unit_tests/test_data.py:26-48,80-96 of the reference: directed edge counts at cutoff 4.0 of ASE's
+    bulk('NaCl', 'rocksalt', a=5.63) primitive cell (36), molecule('H2O') (6), molecule('H') (0)"""
+    from sevenn_b200.neighbors import neighbor_list_brute
+    a = 5.63
+    cell = np.array([[0, a / 2, a / 2], [a / 2, 0, a / 2], [a / 2, a / 2, 0]])
+    ei, ev, _ = neighbor_list_brute(np.array([[0, 0, 0], [a / 2, a / 2, a / 2]]), cell, True, 4.0)
+    assert ei.shape == (2, 36) and ev.shape == (36, 3)
+    h2o = np.array([[0, 0, 0.119262], [0, 0.763239, -0.477047], [0, -0.763239, -0.477047]])
+    ei, ev, _ = neighbor_list_brute(h2o, np.zeros((3, 3)), False, 4.0)
+    assert ei.shape == (2, 6)
+    ei, ev, _ = neighbor_list_brute(np.zeros((1, 3)), np.zeros((3, 3)), False, 4.0)
+    assert ei.shape == (2, 0)
+
+
+def test_neighbor_builders_against_the_definition():
+    """both numpy builders against a direct enumeration of the definition (sevenn/train/dataload.py:32-129: every
+    pair and every lattice translation with |r_j - r_i + S.cell| < cutoff, self-images at S != 0 included),
+    written independently here: a sheared cell thinner than the cutoff, so several images of one pair count"""
+    import itertools
+    from sevenn_b200.neighbors import neighbor_list_brute, neighbor_list_cells
+    rng = np.random.RandomState(5)
+    cell = np.array([[4.1, 0.3, 0.0], [1.2, 4.6, 0.2], [0.4, -0.8, 9.5]])
+    pos = rng.uniform(0, 1, size=(7, 3)) @ cell
+    cutoff = 5.0
+    want = []
+    for i in range(len(pos)):
+        for j in range(len(pos)):
+            for S in itertools.product(range(-3, 4), repeat=3):
+                if i == j and S == (0, 0, 0):
+                    continue
+                d = pos[j] - pos[i] + np.array(S, dtype=float) @ cell
+                if np.linalg.norm(d) < cutoff:
+                    want.append((i, j) + tuple(np.round(d, 9)))
+    want.sort()
+    for build in (lambda: neighbor_list_brute(pos, cell, True, cutoff)[:2], lambda: neighbor_list_cells(pos, cell, cutoff)):
+        ei, ev = build()
+        got = sorted((int(a), int(b)) + tuple(np.round(v, 9)) for a, b, v in zip(ei[0], ei[1], ev))
+        assert len(got) == len(want) > 7 * 20
+        assert np.allclose(np.array(got), np.array(want), atol=1e-8)
+
+
 def test_prepare_params_shapes_and_table_accuracy():
     from sevenn_b200.engine import prepare_params, radial_weights
     meta, arrays = model_weights('sevennet_0')
