@@ -43,6 +43,7 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        self.rows = []
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
@@ -305,32 +306,46 @@ def run_engine(args):
             runner.compute()
 
     # ---- device-resident timing ------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    eng.launch_count(reset=True)
-    sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    for a, b in evs:
-        flush.fill_(1)          # evict L2 between timed iterations (untimed)
+    def timed_run():
+        """W warm-up steps, then exactly K timed steps -> (sum of the step times in ms, max over ranks; launches; clocks)"""
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        a.record()
-        step()
-        b.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop()
-    launches = eng.launch_count()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+        eng.launch_count(reset=True)
+        sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush.fill_(1)          # evict L2 between timed iterations (untimed)
+            if world > 1:
+                dist.barrier()
+            a.record()
+            step()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clk = sampler.stop()
+        n_launch = eng.launch_count()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), n_launch, clk
+
+    # N > 1: the direct-launch schedule (measured at N = 1..8 in round 1 and 2) is timed first, then the same K steps
+    # with the whole step replayed as one CUDA graph (NCCL inside).  Should the graph phase ever hang -- NCCL capture
+    # was only exercised on 2 GPUs while this was written -- a timer prints the line of the direct-launch phase
+    # instead of leaving the run without one.
+    direct, guard = None, None
+    if runner is not None and runner.use_graph:
+        runner.set_cuda_graph(False)
+        d_ms, d_launch, d_clk = timed_run()
+        direct = {'ms_per_step': d_ms / args.steps, 'value': n_atoms * args.steps / (d_ms * 1e-3), 'gpu_launches': int(d_launch)}
+        guard = graph_phase_guard(args, rank, n_atoms, n_edges, cells, direct, d_clk)
+        runner.set_cuda_graph(True)
+    total_ms, launches, clocks = timed_run()
     value = n_atoms * args.steps / (total_ms * 1e-3)
 
     # ---- per-kernel breakdown + roofline of the dominant kernel (rank 0) ---------------------------
@@ -446,9 +461,39 @@ def run_engine(args):
             line['gpu_standin'] = standin
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
+        if direct is not None:
+            line['config']['direct_launch'] = direct       # the same K steps without the whole-step graph
+        if guard is not None:
+            guard.cancel()
         print(json.dumps(line), flush=True)
+    if guard is not None:
+        guard.cancel()
     if world > 1:
         shutdown(runner)
+
+
+def graph_phase_guard(args, rank, n_atoms, n_edges, cells, direct, clocks, deadline_s=420.0):
+    """timer armed before the first whole-step graph capture of a multi-rank run: if the rest of the run does not
+    finish in time, rank 0 prints the line of the direct-launch phase (device-resident number only) and every
+    rank leaves with exit code 0"""
+    def expire():
+        if rank == 0:
+            line = {'metric': METRIC, 'value': direct['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+                    'warmup': max(args.warmup, 3), 'ms_per_step': direct['ms_per_step'], 'higher_is_better': True,
+                    'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                    'config': {'workload': f'{args.model} energy+forces per MD step, diamond Si {cells[0]}x{cells[1]}x{cells[2]} cells = '
+                                           f'{n_atoms} atoms, {n_edges} directed edges, cutoff 5.0 A, positions = lattice + N(0, 0.05 A)',
+                               'parallelism': f'spatial bricks {GRIDS[args.gpus]} + NCCL ghost exchange',
+                               'l2': 'flushed with a 256 MiB write between timed steps', 'cuda_graph': False,
+                               'cuda_graph_note': f'the whole-step graph phase did not finish within {deadline_s:.0f} s; this is the '
+                                                  f'direct-launch phase of the same run (no e2e / parity legs)'},
+                    'e2e': None, 'gpu_launches': direct['gpu_launches'], 'clocks': clocks, 'roofline': None, 'parity': None}
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+    t = threading.Timer(deadline_s, expire)
+    t.daemon = True
+    t.start()
+    return t
 
 
 def shutdown(runner):
