@@ -34,22 +34,11 @@ def _worker(rank, world, port, grid, model, q):
         meta, arrays = model_weights(model)
         pos, cell, z = diamond_si(4, 3, 3, seed=2)
         part = brick_decompose(pos, cell, species_of(meta, z), grid, rank, 5.0)
-        from sevenn_b200.engine import set_option
         run = DistributedRunner(B200Engine(meta, arrays, device=rank), part)
         run.set_cuda_graph(False)
-        set_option('stage_graphs', 0)
-        run.compute()                       # eager stage sequence (split convolutions, overlapped exchanges)
+        run.compute()                       # direct launches: split convolutions, overlapped exchanges
         torch.cuda.synchronize()
         r_eager = run.results()
-        set_option('stage_graphs', 1)
-        for _ in range(3):                  # every stage between two exchanges: captured once, then replayed
-            run.compute()
-        torch.cuda.synchronize()
-        r_stage = run.results()
-        captures, replays = run.engine.stage_graph_stats()
-        assert captures > 0 and replays == 3 * captures, (captures, replays)
-        assert abs(float(r_stage['energy'].cpu()[0]) - float(r_eager['energy'].cpu()[0])) < 1e-9
-        assert torch.allclose(r_stage['forces'], r_eager['forces'], atol=2e-6)
         run.set_cuda_graph(True)
         for _ in range(3):                  # capture, then replays of the whole step incl. the NCCL calls
             run.compute()

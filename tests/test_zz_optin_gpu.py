@@ -195,3 +195,64 @@ def test_host_staged_stage_protocol_two_ranks_on_one_gpu(model):
     assert abs(energy - ref['energy'][0]) < 2e-5
     assert np.allclose(f_all, ref['forces'], atol=5e-6)
     assert np.allclose(virial, ref['virial'], atol=5e-4)
+
+
+def _stage_graph_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    from sevenn_b200.engine import B200Engine, set_option
+    from sevenn_b200.neighbors import diamond_si
+    from sevenn_b200.parallel import DistributedRunner, brick_decompose
+    from helpers import species_of
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        meta, arrays = model_weights('sevennet_0')
+        pos, cell, z = diamond_si(4, 3, 3, seed=2)
+        part = brick_decompose(pos, cell, species_of(meta, z), (2, 1, 1), rank, 5.0)
+        run = DistributedRunner(B200Engine(meta, arrays, device=rank), part, cuda_graph=False, stage_graphs=False)
+        run.compute()
+        torch.cuda.synchronize()
+        ref = run.results()
+        set_option('stage_graphs', 1)       # every stage between two exchanges: captured once, then replayed
+        for _ in range(3):
+            run.compute()
+        torch.cuda.synchronize()
+        out = run.results()
+        captures, replays = run.engine.stage_graph_stats()
+        ok = (captures > 0 and replays == 3 * captures
+              and abs(float(out['energy'].cpu()[0]) - float(ref['energy'].cpu()[0])) < 1e-9
+              and bool(torch.allclose(out['forces'], ref['forces'], atol=2e-6)))
+        q.put((rank, ok, captures, replays))
+    finally:
+        set_option('stage_graphs', 0)
+        dist.destroy_process_group()
+
+
+def test_stage_graphs_between_nccl_exchanges_two_gpus():
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stage_graph_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        res = [q.get(timeout=300) for _ in range(2)]
+        for p in procs:
+            p.join(timeout=120)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    assert all(ok for _, ok, _, _ in res), res
