@@ -184,3 +184,28 @@ def test_cpp_examples_compile(tmp_path):
                     os.path.join(root, 'examples', 'lammps', 'pair_e3gnn_b200.cpp')], check=True)
     subprocess.run(['g++', '-std=c++17', '-fsyntax-only', '-Wall', '-Werror', '-I', os.path.join(root, 'tests', 'mock_lammps'),
                     os.path.join(root, 'examples', 'lammps', 'pair_e3gnn_b200_parallel.cpp')], check=True)
+
+
+def test_bench_graph_phase_guard_prints_the_direct_launch_line():
+    """bench.py at N > 1 times the direct-launch schedule first; if the whole-step graph phase does not finish,
+    a timer prints that phase's line and the process leaves with exit code 0 (never a run without a line)"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import argparse, time, bench\n"
+        "a = argparse.Namespace(gpus=8, steps=20, warmup=5, model='sevennet_0')\n"
+        "d = {'ms_per_step': 6.0, 'value': 100000 / 6.0e-3, 'gpu_launches': 1234}\n"
+        "bench.graph_phase_guard(a, 0, 100000, 2800000, (25, 25, 20), d, {'sm_mhz': 1965.0, 'reasons': []}, deadline_s=0.3)\n"
+        "time.sleep(30)\n"
+        "print('not reached')\n")
+    p = subprocess.run([sys.executable, '-c', code], cwd=root, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1 and 'not reached' not in p.stdout
+    line = json.loads(lines[0])
+    assert line['metric'] == 'atom_updates_per_sec' and line['n_gpus'] == 8 and line['ms_per_step'] == 6.0
+    assert line['config']['cuda_graph'] is False and 'did not finish' in line['config']['cuda_graph_note']
+    for key in ('value', 'unit', 'steps', 'warmup', 'higher_is_better', 'scaling', 'dtype', 'data', 'clocks', 'gpu_launches'):
+        assert key in line
