@@ -99,7 +99,10 @@ S7B_API int s7b_version(void);
  * (force_output.py:198-214).  "concurrent_conv" (default 1): co-schedule the per-l1 convolution kernels.
  * "cuda_graph" (default 1): s7b_engine_compute (and the two *_host entry points built on it) replay a
  * captured CUDA graph of the step instead of issuing its ~75 launches; recaptured automatically when
- * sizes, edge capacity, graph pointers or allocations change. */
+ * sizes, edge capacity, graph pointers or allocations change.  "stage_graphs" (default 0): s7b_engine_run_stage
+ * replays one captured graph per (stage, layer) -- see s7b_engine_stage_graph_stats.  "gate_bwd_rows" (default 0):
+ * the gate backward also leaves the row maxima of dg for the tensor-core linears (saves one pass per layer).
+ * Unknown names return non-zero with s7b_last_error() set. */
 S7B_API int s7b_set_option(const char* name, int value);
 
 /* C[rows, N] = A[rows, K] * W[K, N] (row-major, device pointers) through the same GEMM kernels the
