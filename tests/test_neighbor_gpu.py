@@ -1,5 +1,6 @@
 """Device neighbour list (csrc/neighbor.cuh) vs the numpy builders (which restate the reference's
-matscipy/ASE semantics): identical directed edge multisets, for large / tiny / triclinic / non-periodic
+matscipy/ASE semantics and are themselves pinned on the CPU to the edge counts the reference's tests hold and to a
+direct enumeration of the definition, tests/test_host_logic.py): identical directed edge multisets, for large / tiny / triclinic / non-periodic
 / slab systems; and the positions-in entry point vs the graph-in entry point."""
 import numpy as np
 import pytest
