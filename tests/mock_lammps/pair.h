@@ -12,10 +12,15 @@ struct Error {
   [[noreturn]] void all(const char *, int, const char *);
   [[noreturn]] void one(const char *, int, const char *);
 };
-struct Memory {
-  template <class T> T **create(T **&a, int, int, const char *) { return a; }
-  template <class T> T *create(T *&a, int, const char *) { return a; }
-  template <class T> void destroy(T &) {}
+struct Memory {       // leaks on purpose (test scaffolding): one flat block per array, row pointers for the 2-D form
+  template <class T> T **create(T **&a, int n1, int n2, const char *) {
+    T *flat = new T[(size_t)n1 * n2]();
+    a = new T *[n1];
+    for (int i = 0; i < n1; ++i) a[i] = flat + (size_t)i * n2;
+    return a;
+  }
+  template <class T> T *create(T *&a, int n, const char *) { a = new T[n](); return a; }
+  template <class T> void destroy(T &a) { a = nullptr; }
 };
 struct Atom {
   enum { MAP_NONE = 0, MAP_ARRAY = 1, MAP_HASH = 2, MAP_YES = 3 };

@@ -209,3 +209,20 @@ def test_bench_graph_phase_guard_prints_the_direct_launch_line():
     assert line['config']['cuda_graph'] is False and 'did not finish' in line['config']['cuda_graph_note']
     for key in ('value', 'unit', 'steps', 'warmup', 'higher_is_better', 'scaling', 'dtype', 'data', 'clocks', 'gpu_launches'):
         assert key in line
+
+
+def test_lammps_pair_styles_in_the_mock_harness(tmp_path):
+    """examples/lammps/pair_e3gnn_b200{,_parallel}.cpp run inside tests/mock_lammps/harness_parallel.cpp: one rank, periodic
+    image ghosts, a full neighbour list with skin, stock Comm forward/reverse through the pair style's own pack/unpack
+    hooks, against a CPU double of the stage protocol (stub_s7b.cpp).  Graph with ghost rows + exchanges between the
+    stages must equal the ghost-free evaluation: energy, per-atom energies, forces after the newton reverse sum, virial
+    in LAMMPS component order."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mock, ex = os.path.join(root, 'tests', 'mock_lammps'), os.path.join(root, 'examples', 'lammps')
+    exe = str(tmp_path / 'harness_parallel')
+    subprocess.run(['g++', '-std=c++17', '-O1', '-Wall', '-Werror', '-I', mock, '-I', ex, os.path.join(mock, 'harness_parallel.cpp'),
+                    os.path.join(ex, 'pair_e3gnn_b200_parallel.cpp'), os.path.join(ex, 'pair_e3gnn_b200.cpp'),
+                    os.path.join(mock, 'stub_s7b.cpp'), '-o', exe], check=True)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and p.stdout.strip().endswith('OK'), p.stdout + p.stderr
