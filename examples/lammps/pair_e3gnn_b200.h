@@ -7,8 +7,9 @@
  * 302-411): metal units, `newton_pair on`, a full neighbour list, an atom map (`atom_modify map yes`),
  * one process.  The model file comes from sevenn_b200/export.py:export_flat instead of `sevenn
  * get_model` (TorchScript); there is no libtorch in this pair style.
- * Written against LAMMPS stable_2Aug2023; this repository only syntax-checks it against the minimal
- * declarations in tests/mock_lammps/ (tests/test_host_logic.py) because LAMMPS is not in the image. */
+ * Written against LAMMPS stable_2Aug2023.  LAMMPS is not in the image: this repository compiles it against the
+ * minimal declarations in tests/mock_lammps/ and runs it there on the CPU against a toy double of the library
+ * (tests/mock_lammps/harness_parallel.cpp, tests/test_host_logic.py). */
 #ifdef PAIR_CLASS
 // clang-format off
 PairStyle(e3gnn/b200, PairE3GNNB200)

@@ -11,7 +11,9 @@
  * pack/unpack hooks -- no patched comm_brick.cpp (the reference adds two methods to it,
  * comm_brick.cpp:1057-1123).  Rows travel through host buffers like the reference's without CUDA-aware MPI
  * (pair_e3gnn_parallel.cpp:698-799): s7b_engine_read_rows_host / s7b_engine_write_rows_host.
- * Written against LAMMPS stable_2Aug2023; only syntax-checked here (tests/mock_lammps, tests/test_host_logic.py). */
+ * Written against LAMMPS stable_2Aug2023.  LAMMPS is not in the image: compiled against tests/mock_lammps/ and run there
+ * on the CPU (one rank, periodic image ghosts, stock Comm hooks) against a toy double of the stage protocol
+ * (tests/mock_lammps/harness_parallel.cpp, tests/test_host_logic.py). */
 #ifdef PAIR_CLASS
 // clang-format off
 PairStyle(e3gnn/b200/parallel, PairE3GNNB200Parallel)

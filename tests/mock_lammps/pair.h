@@ -1,5 +1,5 @@
 // Minimal stand-ins for the LAMMPS declarations examples/lammps/pair_e3gnn_b200.cpp uses, only so that
-// the pair style can be syntax-checked without LAMMPS (g++ -fsyntax-only).  Not LAMMPS code: member
+// the pair styles can be compiled and run in the CPU harness (harness_parallel.cpp) without LAMMPS.  Not LAMMPS code: member
 // names and signatures follow the public LAMMPS developer documentation (stable_2Aug2023).
 #pragma once
 #include <cstdint>
