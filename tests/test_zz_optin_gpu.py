@@ -256,3 +256,25 @@ def test_stage_graphs_between_nccl_exchanges_two_gpus():
             if p.is_alive():
                 p.kill()
     assert all(ok for _, ok, _, _ in res), res
+
+
+def test_lammps_pair_styles_in_the_mock_harness_with_the_real_library(tmp_path):
+    """tests/mock_lammps/harness_parallel.cpp built with -DREAL_ENGINE: both pair styles go through settings() /
+    coeff() with an exported model file and run on the GPU inside the mock LAMMPS (64 Si atoms + ~460 periodic image
+    ghosts, stock Comm hooks); reference = the library's positions-in entry on the periodic cell.  (The same harness
+    runs on the CPU against a toy double of the stage protocol in tests/test_host_logic.py.)"""
+    import os
+    import subprocess
+    from helpers import ROOT
+    from sevenn_b200.export import export_flat
+    mock, ex = os.path.join(ROOT, 'tests', 'mock_lammps'), os.path.join(ROOT, 'examples', 'lammps')
+    lib_dir = os.path.join(ROOT, 'sevenn_b200', 'lib')
+    exe = str(tmp_path / 'harness_real')
+    subprocess.check_call(['g++', '-std=c++17', '-O1', '-DREAL_ENGINE', '-I', mock, '-I', ex, os.path.join(mock, 'harness_parallel.cpp'),
+                           os.path.join(ex, 'pair_e3gnn_b200_parallel.cpp'), os.path.join(ex, 'pair_e3gnn_b200.cpp'), '-o', exe,
+                           f'-L{lib_dir}', '-lsevenn_b200', f'-Wl,-rpath,{lib_dir}'])
+    meta, arrays = model_weights('sevennet_0')
+    model = str(tmp_path / 'sevennet_0.s7b')
+    export_flat(model, meta, arrays)
+    p = subprocess.run([exe, model], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip().endswith('OK'), p.stdout + p.stderr
