@@ -89,6 +89,7 @@ def main():
               f'{(tot.max() - tot.min()) / len(pos):.2e} eV/atom, kinetic range {(hist[:, 1].max() - hist[:, 1].min()) / len(pos):.2e} eV/atom; '
               f'CUDA graph (captures, replays) = {eng.graph_stats()}', flush=True)
     if world > 1:
+        driver.runner.close()           # a captured step graph would pin the NCCL communicator
         dist.barrier()
         dist.destroy_process_group()
 
