@@ -336,6 +336,11 @@ class DistributedRunner:
             from .engine import set_option
             set_option('stage_graphs', 1 if self.stage_graphs else 0)
         self._graph, self._graph_key, self.graph_error = None, None, None
+        if self.use_graph:                  # interpreter exit without close(): release the graph before c10d tears NCCL down
+            import atexit
+            import weakref
+            ref = weakref.ref(self)
+            atexit.register(lambda: ref() is not None and ref().close())
         self._graph_ptrs = None             # device addresses of the graph arrays the engine currently reads
         self.graph_captures = self.graph_replays = 0
 
@@ -444,6 +449,13 @@ class DistributedRunner:
             self.graph_error = f'{type(ex).__name__}: {ex}'[:300]
             self._graph, self.use_graph = None, False
             torch.cuda.synchronize(self.device)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     def close(self):
         """drop the captured step graph (it pins the NCCL communicator); call before destroy_process_group()"""
