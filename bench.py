@@ -313,7 +313,7 @@ def run_engine(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        eng.launch_count(reset=True)
+        (runner or eng).launch_count(reset=True)
         sampler.start()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         torch.cuda.synchronize()
@@ -328,7 +328,7 @@ def run_engine(args):
         if world > 1:
             dist.barrier()
         clk = sampler.stop()
-        n_launch = eng.launch_count()
+        n_launch = (runner or eng).launch_count()      # replays of the captured step count the kernels recorded in it
         ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -609,6 +609,7 @@ def run_nacl_d3(args):
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    (eng if world == 1 else runner).launch_count(reset=True)
     total = 0.0
     t_net = t_d3 = 0.0
     for _ in range(args.steps):
@@ -635,6 +636,7 @@ def run_nacl_d3(args):
         t_net += a.elapsed_time(b)
         t_d3 += b.elapsed_time(c)
     clocks = sampler.stop()
+    launches = (eng if world == 1 else runner).launch_count()      # network kernels; the three D3 stages add 8 launches per step
     tt = torch.tensor([total, t_net, t_d3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -674,7 +676,7 @@ def run_nacl_d3(args):
                            'l2': 'flushed with a 256 MiB write between timed steps',
                            'note': 'the reference D3 is single-GPU, O(N^2) and capped at 46 340 atoms; this cell exceeds it'},
                 'ms_network': t_net / args.steps, 'ms_d3': t_d3 / args.steps, 'energy_network_eV': e_net, 'energy_d3_eV': e_d3,
-                'clocks': clocks, 'parity': parity}
+                'gpu_launches': int(launches), 'clocks': clocks, 'parity': parity}
         print(json.dumps(line), flush=True)
     if world > 1:
         shutdown(runner)

@@ -343,6 +343,8 @@ class DistributedRunner:
             atexit.register(lambda: ref() is not None and ref().close())
         self._graph_ptrs = None             # device addresses of the graph arrays the engine currently reads
         self.graph_captures = self.graph_replays = 0
+        self.graph_launches_per_replay = 0
+        self._replayed_launches = 0
 
     def _buf(self, name, t, width):
         return self.engine.buffer(name, t, shape=(self.n_nodes, width))
@@ -441,8 +443,12 @@ class DistributedRunner:
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
+            counted = hasattr(self.engine, 'launch_count')
+            n0 = self.engine.launch_count() if counted else 0
             with torch.cuda.graph(g, stream=side):
                 self._step()
+            # kernels of this library recorded into the graph (the library counts a launch when it issues it)
+            self.graph_launches_per_replay = (self.engine.launch_count() - n0) if counted else 0
             self._graph, self._graph_key = g, self._key()
             self.graph_captures += 1
         except Exception as ex:   # noqa: BLE001
@@ -477,9 +483,18 @@ class DistributedRunner:
             if self._graph is not None:
                 self._graph.replay()
                 self.graph_replays += 1
+                self._replayed_launches += self.graph_launches_per_replay
                 return self
         self._step()
         return self
+
+    def launch_count(self, reset: bool = False) -> int:
+        """kernels of the library launched by this rank since the last reset: those the engine issued directly plus,
+        for every replay of the captured step, the number recorded at capture time"""
+        n = int(self.engine.launch_count(reset)) + self._replayed_launches
+        if reset:
+            self._replayed_launches = 0
+        return n
 
     def results(self):
         eng = self.engine
