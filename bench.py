@@ -636,7 +636,7 @@ def run_nacl_d3(args):
         t_net += a.elapsed_time(b)
         t_d3 += b.elapsed_time(c)
     clocks = sampler.stop()
-    launches = (eng if world == 1 else runner).launch_count()      # network kernels; the three D3 stages add 8 launches per step
+    launches = (eng if world == 1 else runner).launch_count()      # network kernels only (the D3 library entry points do not feed this counter)
     tt = torch.tensor([total, t_net, t_d3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
