@@ -239,7 +239,7 @@ def extra_model(args, model, cells, flush, dev, local_rank, parity_device):
         flush.fill_(1)
         eng.compute()
     torch.cuda.synchronize()
-    roof, breakdown = roofline_from_profile(eng, eng.profile(), ei.shape[1], len(z))
+    roof, breakdown = roofline_from_profile(eng, eng.profile(), ei.shape[1], len(z), 3)
     eng.set_profiling(False)
     out = {'model': model, 'atoms': len(z), 'edges': int(ei.shape[1]), 'ms_per_step': ms, 'value': len(z) / (ms * 1e-3),
            'unit': UNIT, 'roofline': roof, 'kernel_breakdown_ms': breakdown, 'energy_eV': energy}
@@ -361,7 +361,7 @@ def run_engine(args):
     torch.cuda.synchronize()
     if rank == 0:
         prof = eng.profile()
-        roofline, breakdown = roofline_from_profile(eng, prof, n_edges if world == 1 else n_edges_local, eng.n_local)
+        roofline, breakdown = roofline_from_profile(eng, prof, n_edges if world == 1 else n_edges_local, eng.n_local, min(args.steps, 10))
     eng.set_profiling(False)
     if runner is not None:
         runner.set_cuda_graph(graph_on)
@@ -682,7 +682,7 @@ def run_nacl_d3(args):
         shutdown(runner)
 
 
-def roofline_from_profile(eng, prof, n_edges, n_dst):
+def roofline_from_profile(eng, prof, n_edges, n_dst, steps):
     """Roofline of the dominant kernel from the engine's CUDA-event profile.
     The convolution kernels keep x (23 MB) and the radial tables (23 MB/layer) L2-resident, so their
     ALGORITHMIC HBM bytes are only the streamed per-edge records/harmonics/accumulators and the per-atom
@@ -692,7 +692,8 @@ def roofline_from_profile(eng, prof, n_edges, n_dst):
     pipe peak 148 SM x 128 lanes x 2 x SM clock)."""
     if not prof:
         return None, None
-    steps = max(c for _, c in prof.values())
+    # per profiled STEP, not per call: the split schedule of the multi-GPU runner launches a convolution label twice
+    # per step (interior + boundary range)
     breakdown = {k: v[0] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     name = next(iter(breakdown))
     ms = breakdown[name]
