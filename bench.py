@@ -487,7 +487,9 @@ def graph_phase_guard(args, rank, n_atoms, n_edges, cells, direct, clocks, deadl
                                'l2': 'flushed with a 256 MiB write between timed steps', 'cuda_graph': False,
                                'cuda_graph_note': f'the whole-step graph phase did not finish within {deadline_s:.0f} s; this is the '
                                                   f'direct-launch phase of the same run (no e2e / parity legs)'},
-                    'e2e': None, 'gpu_launches': direct['gpu_launches'], 'clocks': clocks, 'roofline': None, 'parity': None}
+                    'e2e': {'value': None, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0,
+                            'note': 'not measured: the run ended in the fallback of the graph-phase guard'},
+                    'gpu_launches': direct['gpu_launches'], 'clocks': clocks, 'roofline': None, 'parity': None}
             print(json.dumps(line), flush=True)
         os._exit(0)
     t = threading.Timer(deadline_s, expire)
