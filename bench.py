@@ -472,7 +472,7 @@ def run_engine(args):
         shutdown(runner)
 
 
-def graph_phase_guard(args, rank, n_atoms, n_edges, cells, direct, clocks, deadline_s=420.0):
+def graph_phase_guard(args, rank, n_atoms, n_edges, cells, direct, clocks, deadline_s=240.0):
     """timer armed before the first whole-step graph capture of a multi-rank run: if the rest of the run does not
     finish in time, rank 0 prints the line of the direct-launch phase (device-resident number only) and every
     rank leaves with exit code 0"""
