@@ -266,7 +266,7 @@ def run_engine(args):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         import datetime
-        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=600))
 
     from sevenn_b200.engine import set_option
     for opt in ('concurrent_conv', 'tc_gemm', 'cuda_graph', 'tc_swizzle'):   # A/B switches: S7B_CONCURRENT_CONV=0, S7B_TC_GEMM=1, S7B_CUDA_GRAPH=0
@@ -573,7 +573,7 @@ def run_nacl_d3(args):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         import datetime
-        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=300))
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=600))
     meta, arrays = load_weights(os.path.join(ROOT, 'weights', 'sevennet_0.npz'))
     tm = {int(k): int(v) for k, v in meta['type_map'].items()}
     cells = (25, 25, 10) if args.cells is None else tuple(args.cells)
