@@ -123,6 +123,10 @@ void PairE3GNNB200::compute(int eflag, int vflag) {
     }
   }
 
+  if (vflag_atom && !atomic_virial_on) {       // per-atom virial on demand (pair_e3gnn.cpp:263-275)
+    if (s7b_engine_set_atomic_virial(engine, 1)) error->one(FLERR, s7b_last_error());
+    atomic_virial_on = true;
+  }
   forces.resize((size_t)nlocal * 3);
   eatom_buf.resize(nlocal);
   double energy = 0.0, v6[6] = {0, 0, 0, 0, 0, 0};
@@ -149,5 +153,13 @@ void PairE3GNNB200::compute(int eflag, int vflag) {
     virial[4] += v6[5];
     virial[5] += v6[4];
   }
-  if (vflag_atom) error->all(FLERR, "e3gnn/b200: per-atom virial needs s7b_set_option(\"atomic_virial\", 1) before pair_coeff");
+  if (vflag_atom) {
+    // the library's per-atom virial: -(v (x) f_e) of every edge on its NEIGHBOUR atom, order xx yy zz xy yz zx -- the
+    // quantity the reference scatters onto edge_idx_dst and negates (pair_e3gnn.cpp:231-275)
+    vatom_buf.resize((size_t)nlocal * 6);
+    if (s7b_engine_read_rows_host(engine, "atomic_virial", 0, 0, nlocal, 6, vatom_buf.data(), nullptr)) error->one(FLERR, s7b_last_error());
+    const int lm[6] = {0, 1, 2, 3, 5, 4};      // LAMMPS (xx, yy, zz, xy, xz, yz)
+    for (int r = 0; r < nlocal; ++r)
+      for (int q = 0; q < 6; ++q) vatom[ilist[r]][q] += vatom_buf[(size_t)r * 6 + lm[q]];
+  }
 }

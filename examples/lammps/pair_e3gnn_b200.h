@@ -44,7 +44,8 @@ class PairE3GNNB200 : public Pair {
   int *species_of_type = nullptr;     // LAMMPS type -> species index of the model
   // host staging, reused between steps
   std::vector<int> species, edge_centre, edge_neighbour, row_of_atom;
-  std::vector<float> edge_vec, forces, eatom_buf;
+  std::vector<float> edge_vec, forces, eatom_buf, vatom_buf;
+  bool atomic_virial_on = false;
 };
 
 }  // namespace LAMMPS_NS

@@ -215,6 +215,10 @@ void PairE3GNNB200Parallel::compute(int eflag, int vflag) {
   for (int r = 0; r < n_rows; ++r) species[r] = species_of_type[type[atom_of_row[r]]];
   atom_rows.resize((size_t)std::max(nall, 1) * comm_width);
 
+  if (vflag_atom && !atomic_virial_on) {       // per-atom virial on demand (pair_e3gnn.cpp:263-275)
+    if (s7b_engine_set_atomic_virial(engine, 1)) error->one(FLERR, s7b_last_error());
+    atomic_virial_on = true;
+  }
   if (s7b_engine_set_graph_host(engine, n_rows, n_owned, (int64_t)edge_centre.size(), species.data(), edge_centre.data(),
                                 edge_neighbour.data(), edge_vec.data(), nullptr))
     error->one(FLERR, s7b_last_error());
@@ -264,5 +268,13 @@ void PairE3GNNB200Parallel::compute(int eflag, int vflag) {
     virial[4] += v6[5];
     virial[5] += v6[4];
   }
-  if (vflag_atom) error->all(FLERR, "e3gnn/b200/parallel: per-atom virial needs s7b_set_option(\"atomic_virial\", 1) before pair_coeff");
+  if (vflag_atom) {
+    // per-atom virial: -(v (x) f_e) of every edge on its NEIGHBOUR row (owned or ghost), order xx yy zz xy yz zx; the
+    // ghost parts are summed into their owners by the reverse communication of the compute that asked for vatom
+    row_stage.resize((size_t)std::max(n_rows, 1) * 6);
+    if (s7b_engine_read_rows_host(engine, "atomic_virial", 0, 0, n_rows, 6, row_stage.data(), nullptr)) error->one(FLERR, s7b_last_error());
+    const int lm[6] = {0, 1, 2, 3, 5, 4};      // LAMMPS (xx, yy, zz, xy, xz, yz)
+    for (int r = 0; r < n_rows; ++r)
+      for (int q = 0; q < 6; ++q) vatom[atom_of_row[r]][q] += row_stage[(size_t)r * 6 + lm[q]];
+  }
 }

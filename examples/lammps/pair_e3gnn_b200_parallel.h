@@ -65,6 +65,7 @@ class PairE3GNNB200Parallel : public Pair {
   // per-atom staging of the row being exchanged: [nlocal + nghost, comm_width] (LAMMPS atom index)
   int comm_width = 0;
   std::vector<float> atom_rows, row_stage;
+  bool atomic_virial_on = false;
 };
 
 }  // namespace LAMMPS_NS

@@ -178,12 +178,16 @@ int main(int argc, char **argv) {
   NeighList list{n, ilist.data(), numneigh.data(), firstneigh.data()};
 
   std::vector<double> eatom(nall, 0.0);
+  std::vector<double> vflat((size_t)nall * 6, 0.0), vflat_s((size_t)nall * 6, 0.0);
+  std::vector<double *> vrow(nall), vrow_s(nall);
+  for (int i = 0; i < nall; ++i) { vrow[i] = &vflat[6 * (size_t)i]; vrow_s[i] = &vflat_s[6 * (size_t)i]; }
   double e_pair = 0, v_pair[6];
   try {
     TestPair pair(&atom);
     pair.set_list(&list);
     pair.eatom = eatom.data();
-    pair.compute(3, 1);
+    pair.vatom = vrow.data();
+    pair.compute(3, 3);
     e_pair = pair.eng_vdwl;
     for (int q = 0; q < 6; ++q) v_pair[q] = pair.virial[q];
   } catch (const std::exception &ex) {
@@ -200,7 +204,8 @@ int main(int argc, char **argv) {
       TestSerialPair sp(&atom);
       sp.set_list(&list);
       sp.eatom = eatom_s.data();
-      sp.compute(3, 1);
+      sp.vatom = vrow_s.data();
+      sp.compute(3, 3);
       e_serial = sp.eng_vdwl;
       for (int q = 0; q < 6; ++q) v_serial[q] = sp.virial[q];
     } catch (const std::exception &ex) {
@@ -239,6 +244,7 @@ int main(int argc, char **argv) {
     s7b_engine_destroy(m.engine);
   }
   const double tolE = 2e-4, tolF = 1e-4, tolV = 5e-3, tolEa = 2e-5;
+  std::vector<float> av_ref;              // the positions-in entry returns no per-atom virial: only the sum rule is checked
 #else
   // the same toy model on the ghost-free graph
   std::vector<int> species(n), centre, nbr;
@@ -257,6 +263,7 @@ int main(int argc, char **argv) {
   for (int t = 0; t <= kLayers; ++t) { d.n_l[t] = 1; d.muls[t][0] = kWidth; }
   S7bEngine *ref = nullptr;
   s7b_engine_create(&d, &ref);
+  s7b_engine_set_atomic_virial(ref, 1);
   if (s7b_engine_set_graph_host(ref, n, n, (int64_t)centre.size(), species.data(), centre.data(), nbr.data(), vec.data(), nullptr)) {
     std::printf("FAIL reference graph: %s\n", s7b_last_error());
     return 1;
@@ -269,8 +276,9 @@ int main(int argc, char **argv) {
     if (t > 0) s7b_engine_run_stage(ref, S7B_STAGE_BWD_LAYER_B, t, nullptr);
   }
   s7b_engine_run_stage(ref, S7B_STAGE_BWD_END, 0, nullptr);
-  std::vector<float> f_ref((size_t)n * 3), e_ref_atom(n);
+  std::vector<float> f_ref((size_t)n * 3), e_ref_atom(n), av_ref((size_t)n * 6);
   double e_ref = 0, v_ref[6];
+  s7b_engine_read_rows_host(ref, "atomic_virial", 0, 0, n, 6, av_ref.data(), nullptr);
   s7b_engine_read_rows_host(ref, "forces", 0, 0, n, 3, f_ref.data(), nullptr);
   s7b_engine_read_rows_host(ref, "atomic_energy", 0, 0, n, 1, e_ref_atom.data(), nullptr);
   s7b_engine_read_scalars_host(ref, &e_ref, v_ref, nullptr);
@@ -287,11 +295,36 @@ int main(int argc, char **argv) {
   for (size_t q = 0; q < f_serial.size(); ++q) dfs = std::fmax(dfs, std::fabs(f_serial[q] - f_ref[q]));
   for (int q = 0; q < 6; ++q) dvs = std::fmax(dvs, std::fabs(v_serial[q] - v_ref[lm[q]]));
   for (int i = 0; i < n; ++i) deas = std::fmax(deas, std::fabs(eatom_s[i] - e_ref_atom[i]));
+  // per-atom virial: ghosts folded into their owners (what the reverse communication of compute stress/atom does);
+  // must sum to the global virial and, in stub mode, equal the ghost-free per-atom values
+  double dva = 0, dvas = 0, dsum = 0, dsum_s = 0;
+  {
+    std::vector<double> va((size_t)n * 6, 0.0), vas((size_t)n * 6, 0.0);
+    for (int i = 0; i < nall; ++i)
+      for (int q = 0; q < 6; ++q) {
+        va[6 * (size_t)(i < n ? i : owner[i - n]) + q] += vflat[6 * (size_t)i + q];
+        vas[6 * (size_t)(i < n ? i : owner[i - n]) + q] += vflat_s[6 * (size_t)i + q];
+      }
+    for (int q = 0; q < 6; ++q) {
+      double t = 0, ts = 0;
+      for (int i = 0; i < n; ++i) { t += va[6 * (size_t)i + q]; ts += vas[6 * (size_t)i + q]; }
+      dsum = std::fmax(dsum, std::fabs(t - v_pair[q]));
+      dsum_s = std::fmax(dsum_s, std::fabs(ts - v_serial[q]));
+    }
+    if (!av_ref.empty())
+      for (int i = 0; i < n; ++i)
+        for (int q = 0; q < 6; ++q) {
+          dva = std::fmax(dva, std::fabs(va[6 * (size_t)i + q] - av_ref[6 * (size_t)i + lm[q]]));
+          dvas = std::fmax(dvas, std::fabs(vas[6 * (size_t)i + q] - av_ref[6 * (size_t)i + lm[q]]));
+        }
+  }
+  std::printf("per-atom virial: |sum - virial| %.2e (parallel) %.2e (serial); vs ghost-free per atom %.2e / %.2e\n", dsum, dsum_s, dva, dvas);
   std::printf("serial style: |dE| %.2e  max|dF| %.2e  max|dV| %.2e  max|dEatom| %.2e\n", des, dfs, dvs, deas);
   std::printf("atoms %d ghosts %d edges %zu  E %.6f  |dE| %.2e  max|dF| %.2e (max|F| %.2e)  max|dV| %.2e  max|dEatom| %.2e\n",
               n, nall - n, centre.size(), e_ref, de, df, fmax, dv, dea);
   const bool ok = de < tolE && df < tolF && dv < tolV && dea < tolEa && fmax > 1e-3 && nall > n && centre.size() > (size_t)n &&
-                  des < tolE && dfs < tolF && dvs < tolV && deas < tolEa;
+                  des < tolE && dfs < tolF && dvs < tolV && deas < tolEa &&
+                  dsum < tolV && dsum_s < tolV && dva < tolV && dvas < tolV;
   std::printf(ok ? "OK\n" : "FAIL\n");
   return ok ? 0 : 1;
 }

@@ -24,7 +24,8 @@ struct S7bEngine {
   std::vector<std::vector<float>> x;      // x[t] : [n_nodes, W], t = 0..T
   std::vector<float> dx;                  // [n_nodes, W]: the rows travelling in the backward
   std::vector<float> g;                   // dE/dx_{t+1} of the owned rows
-  std::vector<float> forces, edge_grad, atomic_energy;
+  std::vector<float> forces, edge_grad, atomic_energy, atomic_virial;
+  bool want_atomic_virial = false;
   double energy = 0.0, virial[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -46,6 +47,7 @@ int s7b_engine_create(const S7bModelDesc* desc, S7bEngine** out) {
 }
 void s7b_engine_destroy(S7bEngine* e) { delete e; }
 int s7b_engine_set_param(S7bEngine*, const char*, int, const float*, size_t) { return 0; }
+int s7b_engine_set_atomic_virial(S7bEngine* e, int enable) { e->want_atomic_virial = enable != 0; return 0; }
 
 int s7b_engine_set_graph_host(S7bEngine* e, int32_t n_nodes, int32_t n_local, int64_t n_edges, const int32_t* species,
                               const int32_t* edge_centre, const int32_t* edge_neighbour, const float* edge_vec, void*) {
@@ -66,6 +68,7 @@ int s7b_engine_set_graph_host(S7bEngine* e, int32_t n_nodes, int32_t n_local, in
   e->forces.assign((size_t)n_nodes * 3, 0.0f);
   e->edge_grad.assign((size_t)n_edges * 3, 0.0f);
   e->atomic_energy.assign(n_local, 0.0f);
+  e->atomic_virial.assign(e->want_atomic_virial ? (size_t)n_nodes * 6 : 0, 0.0f);
   return 0;
 }
 
@@ -130,6 +133,7 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void*) {
     case S7B_STAGE_BWD_END: {
       std::fill(e->forces.begin(), e->forces.end(), 0.0f);
       for (double& v : e->virial) v = 0.0;
+      std::fill(e->atomic_virial.begin(), e->atomic_virial.end(), 0.0f);
       for (int64_t k = 0; k < e->n_edges; ++k) {
         const float* gk = &e->edge_grad[3 * k];          // dE/dv_e, v_e = r_src - r_centre
         const float* v = &e->vec[3 * k];
@@ -137,8 +141,14 @@ int s7b_engine_run_stage(S7bEngine* e, int stage, int t, void*) {
           e->forces[(size_t)e->centre[k] * 3 + a] += gk[a];
           e->forces[(size_t)e->src[k] * 3 + a] -= gk[a];
         }
-        const int ia[6] = {0, 1, 2, 0, 1, 2}, ib[6] = {0, 1, 2, 1, 2, 0};   // xx yy zz xy yz zx of -sum r (x) f, f = -dE/dv
-        for (int q = 0; q < 6; ++q) e->virial[q] += (double)v[ia[q]] * gk[ib[q]];
+        // the engine's conventions (edge_kernels.cuh): f_e = gk is what the centre atom receives; virial6 = -sum v (x) f_e in
+        // the order xx yy zz xy yz zx; the per-atom virial is the same 6-vector, negated, on the NEIGHBOUR row
+        const int ia[6] = {0, 1, 2, 0, 1, 2}, ib[6] = {0, 1, 2, 1, 2, 0};
+        for (int q = 0; q < 6; ++q) {
+          const float w = v[ia[q]] * gk[ib[q]];
+          e->virial[q] -= (double)w;
+          if (e->want_atomic_virial) e->atomic_virial[(size_t)e->src[k] * 6 + q] -= w;
+        }
       }
       return 0;
     }
@@ -152,6 +162,7 @@ static float* buffer(S7bEngine* e, const std::string& nm, int layer, size_t* num
   if (nm == "dx") { *numel = e->dx.size(); *width = e->W; return e->dx.data(); }
   if (nm == "forces") { *numel = e->forces.size(); *width = 3; return e->forces.data(); }
   if (nm == "atomic_energy") { *numel = e->atomic_energy.size(); *width = 1; return e->atomic_energy.data(); }
+  if (nm == "atomic_virial" && e->want_atomic_virial) { *numel = e->atomic_virial.size(); *width = 6; return e->atomic_virial.data(); }
   return nullptr;
 }
 
