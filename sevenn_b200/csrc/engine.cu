@@ -1142,7 +1142,7 @@ static int run_stage_impl(S7bEngine* e, int stage, int t, void* stream) {
       // gate
       // gate; with the tensor-core linears the kernel also leaves the row exponents of h for self_interaction_1 / sc
       const bool h_rows = g_opt_tc_gemm && t + 1 < T && e->layers[t + 1].tcw.count("si1") && e->layers[t + 1].tcw.at("si1") &&
-                          e->layers[t + 1].tcw.at("si1")->ok && L.n_lg * L.n_lg <= 9;      // lmax 3 (16 rows) keeps the separate row pass: not run on hardware yet
+                          e->layers[t + 1].tcw.at("si1")->ok && L.n_lg * L.n_lg <= 16;
       {
         ProfScope ps(e->prof, st, "gate_fwd", t);
         if (h_rows) {
