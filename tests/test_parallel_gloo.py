@@ -270,3 +270,79 @@ def test_device_partition_equals_host_partition(grid, kind):
             ghosts_q = dq['global_ids'][dq['n_local']:][dq['ghost_owner'] == r]
             assert np.array_equal(sent_gids, ghosts_q)
             assert dq['recv_counts'][r] == len(sent_gids)
+
+
+class _PosEngine(FakeEngine, _RowsEngine):
+    """stand-in with the two extra entry points the positions-in runner uses"""
+
+    def set_graph_csr(self, species, rowptr, src, edge_vec, n_local):
+        rp = torch.as_tensor(rowptr).long()
+        centre = torch.repeat_interleave(torch.arange(int(n_local)), rp[1:] - rp[:-1])
+        self.set_graph(species, torch.stack([centre, torch.as_tensor(src).long()]), edge_vec, n_local=int(n_local))
+
+
+def _serial(pos, cell, species):
+    ei, ev = build_graph(pos, cell, True, 5.0)
+    ser = FakeEngine()
+    ser.set_graph(species, ei, ev)
+    for st, ts in [(STAGE_FWD_BEGIN, [0]), (STAGE_FWD_LAYER, range(ser.T)), (STAGE_FWD_END, [0])]:
+        for t in ts:
+            ser.run_stage(st, t)
+    for t in range(ser.T - 1, -1, -1):
+        ser.run_stage(STAGE_BWD_LAYER_A, t)
+        if t > 0:
+            ser.run_stage(STAGE_BWD_LAYER_B, t)
+    ser.run_stage(STAGE_BWD_END)
+    return float(ser.energy[0]), ser.forces.numpy().copy()
+
+
+def _pos_worker(rank, world, port, grid, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        pos, cell, species = _system('si_long')
+        eng = _PosEngine()
+        with DistributedRunner.from_positions(eng, pos, cell, species, grid) as run:
+            run.compute()
+            first = (run.part['global_ids'][:run.n_local].copy(), eng.forces[:run.n_local].numpy().copy(), float(eng.energy[0]))
+            moved = pos + np.random.RandomState(3).normal(scale=0.3, size=pos.shape)     # far enough for atoms to change owner
+            run.update_positions(moved)
+            run.compute()
+            second = (run.part['global_ids'][:run.n_local].copy(), eng.forces[:run.n_local].numpy().copy(), float(eng.energy[0]))
+        q.put((rank, first, second))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_positions_in_runner_repartitions_every_step():
+    """DistributedRunner.from_positions / update_positions (device_brick_partition + GhostExchange.from_lists: send
+    lists derived locally, no handshake) under gloo with a stand-in engine: after the atoms move -- some change
+    owner -- energy and forces still equal the serial evaluation of the moved system"""
+    world, grid = 2, (2, 1, 1)
+    pos, cell, species = _system('si_long')
+    moved = pos + np.random.RandomState(3).normal(scale=0.3, size=pos.shape)
+    refs = [_serial(pos, cell, species), _serial(moved, cell, species)]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pos_worker, args=(r, world, port, grid, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    owners = []
+    for k in range(2):
+        forces = np.zeros((len(pos), 3))
+        seen = np.zeros(len(pos), dtype=int)
+        for rank, first, second in res:
+            gids, f, energy = (first, second)[k]
+            forces[gids] = f
+            seen[gids] += 1
+            assert abs(energy - refs[k][0]) < 1e-6 * abs(refs[k][0])          # edge vectors travel as fp32 here
+        assert (seen == 1).all()
+        assert np.allclose(forces, refs[k][1], atol=1e-5)
+        owners.append({int(g): rank for rank, first, second in res for g in (first, second)[k][0]})
+    assert any(owners[0][g] != owners[1][g] for g in owners[0])               # somebody really changed owner
